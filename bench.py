@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- fused 3-Kinect frames/s of the B200 per-frame point-cloud path.
+
+Workload (BASELINE.json configs[3], "C4"): a synthetic 3-sensor WFOV 1024x1024 depth sequence;
+per frame unproject -> transform -> fuse -> 1 cm voxel -> SOR(20, 2.0) -> floor removal
+(20 cm band, RANSAC 1 cm / 1000 hypotheses, merge, SOR(50, 0.30)) -> point-to-plane ICP refinement
+of both sub extrinsics (1 cm voxel, normals r = 2 cm / 30 nn, max_corr 2 cm, <= 30 iterations).
+A "step" is one batch of --frames-per-step frames per rank; frames are sharded over ranks with no
+collective on the frame path (weak scaling: per-GPU work is fixed).
+
+  python bench.py --gpus 1 --steps K --warmup W            # our arm
+  python bench.py --impl reference ...                     # CPU arm: the oracle port on the host cores
+  torchrun ... bench.py --gpus N ...                       # one rank per GPU
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fused_3kinect_frames_per_s"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="WFOV", choices=["WFOV", "NFOV"])
+    ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--distinct-frames", type=int, default=4, help="synthetic frames rendered per rank (cycled)")
+    ap.add_argument("--streams", type=int, default=4, help="frames in flight per GPU")
+    ap.add_argument("--cpu-sample-frames", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(mode_name, distinct, rank, scale=1e-3):
+    from kinectpy_b200 import synth
+    mode = synth.MODES[mode_name]
+    depth, tab, T = synth.render_sequence(mode, distinct, 3, first_frame=rank * distinct)
+    T_fuse = synth.scale_extrinsics(T, scale)
+    T_icp = np.stack([synth.perturbed_extrinsic(T_fuse[s], 0.3, (3, -3, 3), unit_scale=scale) if s else T_fuse[s]
+                      for s in range(3)])
+    return mode, depth, tab, T_fuse, T_icp
+
+
+def cpu_baseline(cfg, depth, tab, T_fuse, T_icp, frames):
+    """The oracle port (oracle/kp_oracle.c, OpenMP over all host cores) on a bounded sample of the workload."""
+    from oracle import oracle as orc
+    orc.build()
+    t0 = time.perf_counter()
+    tm = {}
+    for f in range(frames):
+        orc.frame_pipeline(cfg, depth[f % depth.shape[0]], tab, T_fuse, T_icp, timings=tm)
+    dt = time.perf_counter() - t0
+    return {"value": frames / dt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+            "sample": "%d frame(s) of the same workload, all stages, oracle/kp_oracle.c with OpenMP" % frames,
+            "seconds": round(dt, 3), "stage_seconds": {k: round(v, 3) for k, v in tm.items()}}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from kinectpy_b200.pipeline import PipelineConfig
+    mode_px = {"WFOV": 1024 * 1024, "NFOV": 640 * 576}[args.mode]
+    cfg = PipelineConfig(n_sensors=3, pixels=mode_px, n_streams=args.streams)
+    workload = ("C4: 3 x %s synthetic depth frames -> unproject+transform+fuse -> voxel 1cm -> SOR(20,2.0) -> "
+                "floor removal (band 20cm, RANSAC 1cm x1000, SOR(50,0.30)) -> p2plane ICP x2 (max_corr 2cm, <=30 it)" % args.mode)
+    config = {"workload": workload, "mode": args.mode, "sensors": 3, "frames_per_step_per_gpu": args.frames_per_step,
+              "distinct_frames": args.distinct_frames, "streams_per_gpu": args.streams, "sharding": "frames round-robin over ranks, no collective",
+              "l2": "flushed between timed steps (256 MiB memset on the timing stream)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU oracle port)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        _, depth, tab, T_fuse, T_icp = make_inputs(args.mode, min(args.distinct_frames, 2), 0)
+        from oracle import oracle as orc
+        orc.build()
+        for _ in range(min(args.warmup, 1)):
+            orc.frame_pipeline(cfg, depth[0], tab, T_fuse, T_icp)
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            orc.frame_pipeline(cfg, depth[s % depth.shape[0]], tab, T_fuse, T_icp)
+        dt = time.perf_counter() - t0
+        val = args.steps / dt
+        cb = {"value": val, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+              "sample": "each step = 1 frame of the workload (bounded sample), oracle/kp_oracle.c with OpenMP on all host threads"}
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from kinectpy_b200 import _cabi
+    from kinectpy_b200.pipeline import FramePipeline
+
+    mode, depth, tab, T_fuse, T_icp = make_inputs(args.mode, args.distinct_frames, rank)
+    S, P, B = 3, mode.pixels, args.frames_per_step
+    pipe = FramePipeline(cfg, tab, T_fuse, T_icp, device=local_rank)
+    ctx = _cabi.default_context(local_rank)
+    batch = np.ascontiguousarray(depth[np.arange(B) % depth.shape[0]])      # uint16 [B,S,P]
+    d_batch = pipe.upload(batch)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile):
+        """K steps, each bracketed by CUDA events on the ctx stream (the step call returns only after its
+        worker streams are drained, so the event pair spans the whole step); L2 flushed between steps."""
+        total_ms = 0.0
+        if profile:
+            pipe.profile(True)
+        for _ in range(steps):
+            ctx.flush_l2()
+            ctx.sync()
+            ctx.timer_start()
+            fn()
+            total_ms += ctx.timer_stop()
+        return total_ms
+
+    step_dev = lambda: pipe.run_raw(d_batch.ptr, True, B)
+    for _ in range(max(args.warmup, 3)):
+        last = step_dev()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = pipe.launch_count()
+    wall0 = time.perf_counter()
+    ms = timed(step_dev, args.steps, profile=True)
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = pipe.launch_count() - l0
+    prof = pipe.profile_read()
+    pipe.profile(False)
+    clocks = sampler.stop()
+
+    # ------------------------------------------------------------------ e2e: host buffers in, clouds out
+    e2e = None
+    if not args.no_e2e:
+        lib = _cabi.load_library()
+        hin, hout = C.c_void_p(), C.c_void_p()
+        stride = S * P
+        assert lib.kp_host_alloc(batch.nbytes, C.byref(hin)) == 0
+        assert lib.kp_host_alloc(B * stride * 12, C.byref(hout)) == 0
+        C.memmove(hin, batch.ctypes.data, batch.nbytes)
+        step_e2e = lambda: pipe.run_host(hin.value, B, hout.value, stride)
+        for _ in range(2):
+            res = step_e2e()
+        barrier()
+        ms_e2e = timed(step_e2e, args.steps, profile=False)
+        barrier()
+        d2h = sum(int(res[f].n_out) * 12 for f in range(B)) + B * C.sizeof(_cabi.FrameResult)
+        e2e = {"ms": ms_e2e, "h2d": int(batch.nbytes), "d2h": int(d2h)}
+        lib.kp_host_free(hin)
+        lib.kp_host_free(hout)
+
+    # ------------------------------------------------------------------ reduce over ranks (max time)
+    if world > 1:
+        t = torch.tensor([ms, e2e["ms"] if e2e else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e_max = float(t[0]), float(t[1])
+    else:
+        ms_e2e_max = e2e["ms"] if e2e else 0.0
+    frames_total = world * B * args.steps
+    value = frames_total / (ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        # per-kernel-family device time (CUDA events on each worker stream, inside the timed region)
+        fam = {k: v for k, v in prof.items()}
+        tot_ms = sum(v["ms"] for v in fam.values()) or 1.0
+        table = {}
+        for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+            gbs = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0
+            table[k] = {"ms_per_frame": round(v["ms"] / (B * args.steps), 4), "share": round(v["ms"] / tot_ms, 4),
+                        "calls": v["calls"], "algorithmic_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
+        top = next(iter(table)) if table else None
+        roofline = None
+        if top:
+            v = fam[top]
+            ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+            roofline = {"kernel": top, "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
+                        "frac": round(ach / peak, 5), "traffic": None, "peak_source": peak_src,
+                        "avg_launch_group_ms": round(v["ms"] / max(v["calls"], 1), 4),
+                        "note": "dominant family by summed device time; neighbour search is latency/ALU-bound, see DESIGN.md"}
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(cfg, depth, tab, T_fuse, T_icp, args.cpu_sample_frames)
+        r0 = last[0]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 decisions on f32 storage", "data": "synthetic", "config": config,
+            "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": round(wall, 3),
+            "e2e": None if e2e is None else {"value": frames_total / (ms_e2e_max * 1e-3), "unit": UNIT,
+                                             "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                                             "ms_per_step": ms_e2e_max / args.steps},
+            "roofline": roofline, "kernels": table, "cpu_baseline": cb,
+            "frame_stats": {"n_fused": int(r0.n_fused), "n_voxel": int(r0.n_voxel), "n_sor": int(r0.n_sor),
+                            "n_floor_inliers": int(r0.n_floor_inliers), "n_out": int(r0.n_out),
+                            "icp_iters": [int(r0.icp_iters[i]) for i in range(2)],
+                            "icp_fitness": [round(float(r0.icp_fitness[i]), 4) for i in range(2)]},
+        }
+        print(json.dumps(line))
+    pipe.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

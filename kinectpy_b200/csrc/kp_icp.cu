@@ -1,0 +1,267 @@
+// kp_icp.cu -- K5: point-to-plane ICP, every iteration on the device.
+// Replaces o3d.pipelines.registration.registration_icp(source, target, max_corr, init,
+// TransformationEstimationPointToPlane()) at preprocessing/registration.py:78-84.
+//
+// One kernel launch per pass.  A pass (i) applies the update found by the previous pass to the
+// moving copy of the source (double, in place, like upstream's pcd.Transform(update)),
+// (ii) finds each source point's nearest target point inside max_corr through the target's grid
+// hash (27 cells, z-rows merged, one thread per source point), (iii) accumulates the 21+6+2
+// normal-equation scalars in double per thread, reduces them with warp shuffles, then a
+// shared-memory tree per CTA, then per-CTA slots; (iv) the last CTA to finish (integer ticket)
+// adds the slots in slot order, evaluates fitness / rmse / the convergence test, solves the 6x6
+// system, composes T and publishes the next update and a `done` flag.  The host enqueues
+// max_iter+1 passes without reading anything back; passes after `done` return immediately.
+#include <math.h>
+#include <string.h>
+#include "kp_grid.cuh"
+
+namespace {
+constexpr int ICP_THREADS = 256;
+constexpr int ICP_NV = 29;   // 21 upper-triangular JtJ + 6 Jtr + sum d^2 + count
+
+struct IcpState {
+    double T[16];
+    double U[16];
+    double fitness, rmse;
+    long long ncorr;
+    int done, iters;
+    unsigned int ticket;
+    int pad;
+};
+
+struct IcpParams {
+    KpGridDev g;
+    const float *tgt_normals;   // indexed by original target index
+    double *cur;                // [ns][3] moving source
+    int ns;
+    double r2;
+    int pass, max_iter;
+    double rel_fit, rel_rmse;
+    IcpState *st;
+    double *slots;              // [gridDim.x][ICP_NV]
+};
+
+__global__ void __launch_bounds__(256) k_icp_init(const float *src, int ns, const __grid_constant__ IcpParams p, IcpState init)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *p.st = init;
+    if (i >= ns) return;
+    const double *T = init.T;
+    double X = src[3 * (int64_t)i], Y = src[3 * (int64_t)i + 1], Z = src[3 * (int64_t)i + 2];
+    p.cur[3 * (int64_t)i] = kp_affine(T[0], T[1], T[2], T[3], X, Y, Z);
+    p.cur[3 * (int64_t)i + 1] = kp_affine(T[4], T[5], T[6], T[7], X, Y, Z);
+    p.cur[3 * (int64_t)i + 2] = kp_affine(T[8], T[9], T[10], T[11], X, Y, Z);
+}
+
+__device__ bool icp_solve6(double M[6][7], double *x)
+{
+    for (int c = 0; c < 6; ++c) {
+        int pv = c;
+        double best = fabs(M[c][c]);
+        for (int r = c + 1; r < 6; ++r)
+            if (fabs(M[r][c]) > best) { best = fabs(M[r][c]); pv = r; }
+        if (!(best > 1e-300)) return false;
+        if (pv != c)
+            for (int j = 0; j < 7; ++j) { double t = M[c][j]; M[c][j] = M[pv][j]; M[pv][j] = t; }
+        for (int r = c + 1; r < 6; ++r) {
+            double f = M[r][c] / M[c][c];
+            for (int j = c; j < 7; ++j) M[r][j] -= f * M[c][j];
+        }
+    }
+    for (int r = 5; r >= 0; --r) {
+        double s = M[r][6];
+        for (int j = r + 1; j < 6; ++j) s -= M[r][j] * x[j];
+        x[r] = s / M[r][r];
+        if (!isfinite(x[r])) return false;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(const __grid_constant__ IcpParams p)
+{
+    __shared__ double sh[ICP_THREADS / 32][ICP_NV];
+    __shared__ double tot[ICP_NV];
+    __shared__ unsigned int s_ticket;
+    IcpState *st = p.st;
+    if (st->done) return;
+    const KpGridDev &g = p.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    double U[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) U[i] = st->U[i];
+
+    double acc[ICP_NV];
+#pragma unroll
+    for (int i = 0; i < ICP_NV; ++i) acc[i] = 0.0;
+
+    for (int i = blockIdx.x * ICP_THREADS + tid; i < p.ns; i += gridDim.x * ICP_THREADS) {
+        double sx = p.cur[3 * (int64_t)i], sy = p.cur[3 * (int64_t)i + 1], sz = p.cur[3 * (int64_t)i + 2];
+        if (p.pass > 0) {
+            double x2 = kp_affine(U[0], U[1], U[2], U[3], sx, sy, sz);
+            double y2 = kp_affine(U[4], U[5], U[6], U[7], sx, sy, sz);
+            double z2 = kp_affine(U[8], U[9], U[10], U[11], sx, sy, sz);
+            sx = x2; sy = y2; sz = z2;
+            p.cur[3 * (int64_t)i] = sx; p.cur[3 * (int64_t)i + 1] = sy; p.cur[3 * (int64_t)i + 2] = sz;
+        }
+        if (isnan(sx) || g.dim[0] <= 0) continue;
+        const int cx = kp_cell_coord(g, sx, 0), cy = kp_cell_coord(g, sy, 1), cz = kp_cell_coord(g, sz, 2);
+        double bd = INFINITY;
+        int bi = -1, bpos = -1;
+        for (int dx = -1; dx <= 1; ++dx)
+            for (int dy = -1; dy <= 1; ++dy) {
+                int a = 0x7fffffff, b = 0;
+#pragma unroll
+                for (int dz = -1; dz <= 1; ++dz) {
+                    int2 r = kp_cell_range(g, cx + dx, cy + dy, cz + dz);
+                    if (r.y > r.x) { a = min(a, r.x); b = max(b, r.y); }
+                }
+                for (int t = a; t < b; ++t) {
+                    float4 q = __ldg(g.pts + t);
+                    double d2 = kp_d2(sx, sy, sz, (double)q.x, (double)q.y, (double)q.z);
+                    int id = __float_as_int(q.w);
+                    if (d2 < p.r2 && (d2 < bd || (d2 == bd && id < bi))) { bd = d2; bi = id; bpos = t; }
+                }
+            }
+        if (bi < 0) continue;
+        float4 q = __ldg(g.pts + bpos);
+        const double ex = sx - (double)q.x, ey = sy - (double)q.y, ez = sz - (double)q.z;
+        const double nx = (double)p.tgt_normals[3 * (int64_t)bi], ny = (double)p.tgt_normals[3 * (int64_t)bi + 1],
+                     nz = (double)p.tgt_normals[3 * (int64_t)bi + 2];
+        const double r = (ex * nx + ey * ny) + ez * nz;
+        const double J[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = a; b < 6; ++b) acc[k++] += J[a] * J[b];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * r;
+        acc[27] += bd;
+        acc[28] += 1.0;
+    }
+    // warp shuffle reduction, then a fixed-order sum over the warps of the CTA
+#pragma unroll
+    for (int i = 0; i < ICP_NV; ++i) acc[i] = kp_butterfly_sum(acc[i]);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < ICP_NV; ++i) sh[warp][i] = acc[i];
+    __syncthreads();
+    if (tid < ICP_NV) {
+        double s = 0;
+        for (int w = 0; w < ICP_THREADS / 32; ++w) s += sh[w][tid];
+        p.slots[(size_t)blockIdx.x * ICP_NV + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&st->ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    // ---- last CTA: deterministic cross-CTA sum, solve, update
+    __threadfence();
+    if (tid < ICP_NV) {
+        double s = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(p.slots + (size_t)b * ICP_NV + tid);
+        tot[tid] = s;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    const double nc = tot[28];
+    const double fit = p.ns > 0 ? nc / (double)p.ns : 0.0;
+    const double rmse = nc > 0 ? sqrt(tot[27] / nc) : 0.0;
+    const double pfit = st->fitness, prmse = st->rmse;
+    st->fitness = fit; st->rmse = rmse; st->ncorr = (long long)nc;
+    st->ticket = 0;
+    bool done = false;
+    if (p.pass > 0) {
+        st->iters = p.pass;
+        if (fabs(pfit - fit) < p.rel_fit && fabs(prmse - rmse) < p.rel_rmse) done = true;
+    }
+    if (p.pass == p.max_iter) done = true;
+    if (done) { st->done = 1; return; }
+    double M[6][7];
+    {
+        int k = 0;
+        for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b) { M[a][b] = tot[k]; M[b][a] = tot[k]; ++k; }
+        for (int a = 0; a < 6; ++a) M[a][6] = -tot[21 + a];
+    }
+    double x[6];
+    double Un[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    if (nc > 0 && icp_solve6(M, x)) {
+        double ca = cos(x[0]), sa = sin(x[0]), cb = cos(x[1]), sb = sin(x[1]), cg = cos(x[2]), sg = sin(x[2]);
+        Un[0] = cg * cb; Un[1] = cg * sb * sa - sg * ca; Un[2] = cg * sb * ca + sg * sa; Un[3] = x[3];
+        Un[4] = sg * cb; Un[5] = sg * sb * sa + cg * ca; Un[6] = sg * sb * ca - cg * sa; Un[7] = x[4];
+        Un[8] = -sb;     Un[9] = cb * sa;                Un[10] = cb * ca;               Un[11] = x[5];
+    }
+    double Tn[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s = s + Un[4 * i + k] * st->T[4 * k + j];
+            Tn[4 * i + j] = s;
+        }
+    for (int i = 0; i < 16; ++i) { st->T[i] = Tn[i]; st->U[i] = Un[i]; }
+    __threadfence();
+}
+}  // namespace
+
+// internal form: the target grid is built by the caller (pipeline reuses it for both subs)
+int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &tgt_grid, const float *d_tgt_normals,
+                  double max_corr, const double *h_init16, int max_iter, double rel_fitness, double rel_rmse,
+                  double *h_T_out, double *h_fitness, double *h_rmse, int *h_iters, int64_t *h_ncorr)
+{
+    if (n_src > 2147483000LL) return kp_set_err(ctx, KP_E_ARG, "more than 2^31 points in one call");
+    if (max_iter < 0) max_iter = 0;
+    KpProfScope prof_scope__(ctx, "icp");
+    IcpParams p;
+    p.g = kp_grid_dev(tgt_grid);
+    if (tgt_grid.n <= 0) p.g.dim[0] = p.g.dim[1] = p.g.dim[2] = 0;
+    p.tgt_normals = d_tgt_normals;
+    p.ns = (int)n_src;
+    p.r2 = max_corr * max_corr;
+    p.max_iter = max_iter;
+    p.rel_fit = rel_fitness; p.rel_rmse = rel_rmse;
+    int grid = (int)kp_blocks(n_src > 0 ? n_src : 1, ICP_THREADS);
+    if (grid > ctx->sm_count * 2) grid = ctx->sm_count * 2;
+    KP_TRY(kp_ws(ctx, (size_t)(n_src > 0 ? n_src : 1) * 3, &p.cur));
+    KP_TRY(kp_ws(ctx, (size_t)grid * ICP_NV, &p.slots));
+    KP_TRY(kp_ws(ctx, 1, &p.st));
+    IcpState init;
+    memset(&init, 0, sizeof init);
+    for (int i = 0; i < 16; ++i) { init.T[i] = h_init16[i]; init.U[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+    p.pass = 0;
+    k_icp_init<<<kp_blocks(n_src > 0 ? n_src : 1, 256), 256, 0, ctx->stream>>>(d_src, (int)n_src, p, init);
+    KP_LAUNCH_CHECK(ctx);
+    for (int pass = 0; pass <= max_iter; ++pass) {
+        p.pass = pass;
+        k_icp_pass<<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
+        KP_LAUNCH_CHECK(ctx);
+    }
+    KP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, p.st, sizeof(IcpState), cudaMemcpyDeviceToDevice, ctx->stream));
+    KP_TRY(kp_fetch_scratch(ctx, sizeof(IcpState)));
+    const IcpState *hs = (const IcpState *)ctx->h_scratch;
+    // per executed pass: moving source read + write-back (48 B) and, per match, target point + normal (28 B)
+    prof_scope__.add_bytes((double)(hs->iters + 1) * 76.0 * (double)n_src);
+    if (h_T_out) memcpy(h_T_out, hs->T, sizeof(double) * 16);
+    if (h_fitness) *h_fitness = hs->fitness;
+    if (h_rmse) *h_rmse = hs->rmse;
+    if (h_iters) *h_iters = hs->iters;
+    if (h_ncorr) *h_ncorr = hs->ncorr;
+    return KP_OK;
+}
+
+extern "C" int kp_icp_point_to_plane(kp_ctx *ctx, const float *d_src, int64_t n_src, const float *d_tgt,
+                                     const float *d_tgt_normals, int64_t n_tgt, double max_corr, const double *h_init16,
+                                     int max_iter, double rel_fitness, double rel_rmse, double *h_T_out,
+                                     double *h_fitness, double *h_rmse, int *h_iters, int64_t *h_ncorr)
+{
+    if (!ctx || !h_init16) return kp_set_err(ctx, KP_E_ARG, "kp_icp_point_to_plane: NULL argument");
+    if (!(max_corr > 0.0)) return kp_set_err(ctx, KP_E_ARG, "registration_icp: max_correspondence_distance <= 0");
+    if (!d_tgt_normals) return kp_set_err(ctx, KP_E_ARG, "TransformationEstimationPointToPlane requires target normals");
+    kp_enter(ctx);
+    KpGrid g;
+    KP_TRY(kp_grid_build(ctx, d_tgt, n_tgt, max_corr * (1.0 + 1e-6), nullptr, &g));
+    return kp_icp_device(ctx, d_src, n_src, g, d_tgt_normals, max_corr, h_init16, max_iter, rel_fitness, rel_rmse, h_T_out,
+                         h_fitness, h_rmse, h_iters, h_ncorr);
+}

@@ -1,0 +1,486 @@
+// kp_primitives.cu -- device-wide building blocks written for this library:
+// ordered stream compaction (ballot scan), stable LSD radix sort of (key, index) pairs,
+// run-head extraction, bounds, canonical double sums.  No CUB/Thrust on the product path.
+#include <math.h>
+#include "kp_common.cuh"
+
+// ===================================================== ordered compaction ==
+// Tile = 256 threads x 8 items, striped: item j of thread t is element base + j*256 + t, so the
+// element order inside a tile is (j, warp, lane) and every load is coalesced.  Flags are scanned
+// with ballots: rank inside the warp from popc, then a 64-entry (j, warp) table per tile.
+namespace {
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 8;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
+
+struct FlagMask {
+    const uint8_t *mask; int invert; const float *nan_src;
+    __device__ bool operator()(int64_t i) const
+    {
+        if (mask) return (mask[i] != 0) != (invert != 0);
+        return !isnan(nan_src[3 * i]);
+    }
+};
+template <class K>
+struct FlagRunHead {
+    const K *keys;
+    __device__ bool operator()(int64_t i) const { return i == 0 || keys[i] != keys[i - 1]; }
+};
+struct EmitPos {
+    int32_t *pos_out; int32_t *index_out;
+    __device__ void operator()(int64_t i, bool f, int32_t pos) const
+    {
+        if (pos_out) pos_out[i] = f ? pos : -1;
+        if (f && index_out) index_out[pos] = (int32_t)i;
+    }
+};
+struct EmitRunStart {
+    int32_t *run_start;
+    __device__ void operator()(int64_t i, bool f, int32_t pos) const
+    {
+        if (f) run_start[pos] = (int32_t)i;
+    }
+};
+
+template <class Flag>
+__global__ void __launch_bounds__(SC_THREADS) k_flag_count(int64_t n, Flag flag, int32_t *block_sums)
+{
+    __shared__ int warp_cnt[SC_THREADS / 32];
+    int64_t base = (int64_t)blockIdx.x * SC_TILE;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j) {
+        int64_t i = base + j * SC_THREADS + threadIdx.x;
+        bool f = i < n && flag(i);
+        cnt += __popc(__ballot_sync(KP_FULL, f));   // identical in all lanes of the warp
+    }
+    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < SC_THREADS / 32; ++w) s += warp_cnt[w];
+        block_sums[blockIdx.x] = s;
+    }
+}
+
+// single block: in-place exclusive scan of `nb` int32 values, total to *total
+__global__ void __launch_bounds__(1024) k_scan_block_sums(int32_t *v, int nb, int32_t *total)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        int i = base + threadIdx.x;
+        int x = i < nb ? v[i] : 0;
+        int incl = x;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            int y = __shfl_up_sync(KP_FULL, incl, s);
+            if (lane >= s) incl += y;
+        }
+        if (lane == 31) warp_tot[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            int t = warp_tot[lane];
+            int ti = t;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                int y = __shfl_up_sync(KP_FULL, ti, s);
+                if (lane >= s) ti += y;
+            }
+            warp_tot[lane] = ti - t;   // exclusive warp offsets
+        }
+        __syncthreads();
+        int excl = carry_s + warp_tot[w] + incl - x;
+        if (i < nb) v[i] = excl;
+        __syncthreads();               // everyone has read carry_s and warp_tot
+        if (threadIdx.x == 1023) carry_s = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry_s;
+}
+
+template <class Flag, class Emit>
+__global__ void __launch_bounds__(SC_THREADS) k_flag_scatter(int64_t n, Flag flag, Emit emit, const int32_t *block_off)
+{
+    __shared__ int cnt[SC_ITEMS * (SC_THREADS / 32) + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t base = (int64_t)blockIdx.x * SC_TILE;
+    bool f[SC_ITEMS];
+    int rank[SC_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j) {
+        int64_t i = base + j * SC_THREADS + threadIdx.x;
+        f[j] = i < n && flag(i);
+        unsigned b = __ballot_sync(KP_FULL, f[j]);
+        rank[j] = __popc(b & ((1u << lane) - 1u));
+        if (lane == 0) cnt[j * (SC_THREADS / 32) + w] = __popc(b);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = block_off[blockIdx.x];
+        for (int e = 0; e < SC_ITEMS * (SC_THREADS / 32); ++e) { int c = cnt[e]; cnt[e] = s; s += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j) {
+        int64_t i = base + j * SC_THREADS + threadIdx.x;
+        if (i < n) emit(i, f[j], cnt[j * (SC_THREADS / 32) + w] + rank[j]);
+    }
+}
+
+template <class Flag, class Emit>
+int compact_generic(kp_ctx *ctx, int64_t n, Flag flag, Emit emit, int32_t *d_total)
+{
+    if (n <= 0) {
+        KP_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(int32_t), ctx->stream));
+        return KP_OK;
+    }
+    unsigned nb = kp_blocks(n, SC_TILE);
+    int32_t *d_sums;
+    KP_TRY(kp_ws(ctx, nb, &d_sums));
+    k_flag_count<<<nb, SC_THREADS, 0, ctx->stream>>>(n, flag, d_sums);
+    KP_LAUNCH_CHECK(ctx);
+    k_scan_block_sums<<<1, 1024, 0, ctx->stream>>>(d_sums, (int)nb, d_total);
+    KP_LAUNCH_CHECK(ctx);
+    k_flag_scatter<<<nb, SC_THREADS, 0, ctx->stream>>>(n, flag, emit, d_sums);
+    KP_LAUNCH_CHECK(ctx);
+    return KP_OK;
+}
+
+__global__ void k_gather3(int64_t n, const int32_t *pos, const float *in, float *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = pos[i];
+    if (p < 0) return;
+    float a = in[3 * i], b = in[3 * i + 1], c = in[3 * i + 2];
+    out[3 * (int64_t)p] = a; out[3 * (int64_t)p + 1] = b; out[3 * (int64_t)p + 2] = c;
+}
+}  // namespace
+
+int kp_prim_compact_mask(kp_ctx *ctx, int64_t n, const uint8_t *d_mask, int invert, const float *d_nan_src,
+                         int32_t *d_pos_out, int32_t *d_index_out, int32_t *d_total)
+{
+    KP_PROFB(ctx, "compact_scan", (double)n * (d_mask ? 2.0 + 4.0 : 2.0 * 12.0 + 4.0));
+    FlagMask fl{d_mask, invert, d_nan_src};
+    EmitPos em{d_pos_out, d_index_out};
+    return compact_generic(ctx, n, fl, em, d_total);
+}
+
+int kp_prim_gather3(kp_ctx *ctx, int64_t n, const int32_t *d_pos, const float *d_in, float *d_out)
+{
+    if (n <= 0) return KP_OK;
+    KP_PROFB(ctx, "compact_gather", (double)n * (4.0 + 12.0 + 12.0));
+    k_gather3<<<kp_blocks(n, 256), 256, 0, ctx->stream>>>(n, d_pos, d_in, d_out);
+    KP_LAUNCH_CHECK(ctx);
+    return KP_OK;
+}
+
+int kp_prim_run_starts_u64(kp_ctx *ctx, int64_t n, const uint64_t *d_keys, int32_t *d_run_start, int32_t *d_total)
+{
+    KP_PROFB(ctx, "run_heads", (double)n * 2.0 * 8.0);
+    return compact_generic(ctx, n, FlagRunHead<uint64_t>{d_keys}, EmitRunStart{d_run_start}, d_total);
+}
+int kp_prim_run_starts_u32(kp_ctx *ctx, int64_t n, const uint32_t *d_keys, int32_t *d_run_start, int32_t *d_total)
+{
+    KP_PROFB(ctx, "run_heads", (double)n * 2.0 * 4.0);
+    return compact_generic(ctx, n, FlagRunHead<uint32_t>{d_keys}, EmitRunStart{d_run_start}, d_total);
+}
+
+// ============================================================ radix sort ==
+// Stable LSD sort, 8 bits per pass, three kernels per pass:
+//   hist   : per-tile digit histogram           -> g_hist[digit][tile]
+//   scan   : exclusive scan over (digit, tile)  -> g_hist in place + g_base[digit]
+//   scatter: per-warp stable ranking with __match_any_sync, then direct scatter
+// Tile = 256 threads x RS_ITEMS keys; warp w owns a contiguous slab of RS_ITEMS*32 keys so the
+// order inside a tile is (warp, item, lane) = input order.
+namespace {
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K *keys, int64_t n, int shift, int32_t *g_hist, int nb)
+{
+    __shared__ int hist[256];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        int64_t i = base + j * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&hist[(unsigned)(keys[i] >> shift) & 0xFFu], 1);
+    }
+    __syncthreads();
+    g_hist[(int64_t)threadIdx.x * nb + blockIdx.x] = hist[threadIdx.x];
+}
+
+// single block of 1024 threads (32 warps x 8 digits each)
+__global__ void __launch_bounds__(1024) k_rs_scan(int32_t *g_hist, int nb, int32_t *g_base)
+{
+    __shared__ int tot[256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int dd = 0; dd < 8; ++dd) {
+        int d = w * 8 + dd;
+        int32_t *row = g_hist + (int64_t)d * nb;
+        int carry = 0;
+        for (int base = 0; base < nb; base += 32) {
+            int i = base + lane;
+            int x = i < nb ? row[i] : 0;
+            int incl = x;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                int y = __shfl_up_sync(KP_FULL, incl, s);
+                if (lane >= s) incl += y;
+            }
+            if (i < nb) row[i] = carry + incl - x;
+            carry += __shfl_sync(KP_FULL, incl, 31);
+        }
+        if (lane == 0) tot[d] = carry;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int d = 0; d < 256; ++d) { g_base[d] = s; s += tot[d]; }
+    }
+}
+
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K *keys_in, const int32_t *vals_in, K *keys_out,
+                                                           int32_t *vals_out, int64_t n, int shift,
+                                                           const int32_t *g_hist, const int32_t *g_base, int nb)
+{
+    __shared__ int cnt[RS_WARPS][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < RS_WARPS * 256; e += RS_THREADS) (&cnt[0][0])[e] = 0;
+    __syncthreads();
+    const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * (RS_ITEMS * 32);
+    K kreg[RS_ITEMS];
+    int rank[RS_ITEMS];
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        int64_t i = wbase + j * 32 + lane;
+        bool in = i < n;
+        unsigned act = __ballot_sync(KP_FULL, in);
+        rank[j] = 0;
+        kreg[j] = 0;
+        if (in) {
+            K key = keys_in[i];
+            kreg[j] = key;
+            unsigned d = (unsigned)(key >> shift) & 0xFFu;
+            unsigned peers = __match_any_sync(act, d);
+            int leader = __ffs(peers) - 1;
+            int old = 0;
+            if (lane == leader) { old = cnt[w][d]; cnt[w][d] = old + __popc(peers); }
+            old = __shfl_sync(peers, old, leader);
+            rank[j] = old + __popc(peers & lt);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        int d = threadIdx.x;   // 256 threads <-> 256 digits
+        int off = g_base[d] + g_hist[(int64_t)d * nb + blockIdx.x];
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) { int c = cnt[ww][d]; cnt[ww][d] = off; off += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        int64_t i = wbase + j * 32 + lane;
+        if (i < n) {
+            unsigned d = (unsigned)(kreg[j] >> shift) & 0xFFu;
+            int pos = cnt[w][d] + rank[j];
+            keys_out[pos] = kreg[j];
+            vals_out[pos] = vals_in ? vals_in[i] : (int32_t)i;
+        }
+    }
+}
+
+template <class K>
+int sort_pairs(kp_ctx *ctx, int64_t n, int bits, K *d_keys, K *d_keys_tmp, int32_t *d_vals, int32_t *d_vals_tmp,
+               K **keys_sorted, int32_t **vals_sorted, bool vals_are_iota)
+{
+    *keys_sorted = d_keys;
+    *vals_sorted = d_vals;
+    if (n <= 0) return KP_OK;
+    // algorithmic bytes: ceil(b/8) passes x 2 x (key + 4-byte index) x n, plus one histogram read
+    KP_PROFB(ctx, "radix_sort", (double)n * (((bits + 7) / 8 < 1 ? 1 : (bits + 7) / 8) * 2.0 * (sizeof(K) + 4.0) + sizeof(K)));
+    int nb = (int)kp_blocks(n, RS_TILE);
+    int32_t *g_hist, *g_base;
+    KP_TRY(kp_ws(ctx, (size_t)256 * nb, &g_hist));
+    KP_TRY(kp_ws(ctx, 256, &g_base));
+    int passes = (bits + 7) / 8;
+    if (passes < 1) passes = 1;
+    K *kin = d_keys, *kout = d_keys_tmp;
+    int32_t *vin = d_vals, *vout = d_vals_tmp;
+    for (int p = 0; p < passes; ++p) {
+        int shift = 8 * p;
+        k_rs_hist<K><<<nb, RS_THREADS, 0, ctx->stream>>>(kin, n, shift, g_hist, nb);
+        KP_LAUNCH_CHECK(ctx);
+        k_rs_scan<<<1, 1024, 0, ctx->stream>>>(g_hist, nb, g_base);
+        KP_LAUNCH_CHECK(ctx);
+        k_rs_scatter<K><<<nb, RS_THREADS, 0, ctx->stream>>>(kin, (p == 0 && vals_are_iota) ? nullptr : vin, kout, vout, n,
+                                                            shift, g_hist, g_base, nb);
+        KP_LAUNCH_CHECK(ctx);
+        K *tk = kin; kin = kout; kout = tk;
+        int32_t *tv = vin; vin = vout; vout = tv;
+    }
+    *keys_sorted = kin;
+    *vals_sorted = vin;
+    return KP_OK;
+}
+}  // namespace
+
+// The value of element i entering the first pass is its input position i (iota), synthesised in
+// the scatter kernel instead of being read, so d_vals need not be initialised.
+int kp_prim_sort_pairs_u64(kp_ctx *ctx, int64_t n, int bits, uint64_t *d_keys, uint64_t *d_keys_tmp, int32_t *d_vals,
+                           int32_t *d_vals_tmp, uint64_t **d_keys_sorted, int32_t **d_vals_sorted)
+{
+    return sort_pairs<uint64_t>(ctx, n, bits, d_keys, d_keys_tmp, d_vals, d_vals_tmp, d_keys_sorted, d_vals_sorted, true);
+}
+int kp_prim_sort_pairs_u32(kp_ctx *ctx, int64_t n, int bits, uint32_t *d_keys, uint32_t *d_keys_tmp, int32_t *d_vals,
+                           int32_t *d_vals_tmp, uint32_t **d_keys_sorted, int32_t **d_vals_sorted)
+{
+    return sort_pairs<uint32_t>(ctx, n, bits, d_keys, d_keys_tmp, d_vals, d_vals_tmp, d_keys_sorted, d_vals_sorted, true);
+}
+
+// ================================================================ bounds ==
+namespace {
+__global__ void k_bounds_init(int32_t *enc)
+{
+    if (threadIdx.x < 3) enc[threadIdx.x] = kp_f2ord(INFINITY);
+    else if (threadIdx.x < 6) enc[threadIdx.x] = kp_f2ord(-INFINITY);
+    else if (threadIdx.x < 8) enc[threadIdx.x] = 0;
+}
+__global__ void __launch_bounds__(256) k_bounds(const float *xyz, int64_t n, int32_t *enc)
+{
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int cnt = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        if (isnan(x)) continue;
+        mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+        mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+        ++cnt;
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(KP_FULL, mn[c], s));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(KP_FULL, mx[c], s));
+        }
+        cnt += __shfl_xor_sync(KP_FULL, cnt, s);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            atomicMin(&enc[c], kp_f2ord(mn[c]));
+            atomicMax(&enc[3 + c], kp_f2ord(mx[c]));
+        }
+        atomicAdd(&enc[6], cnt);
+    }
+}
+}  // namespace
+
+int kp_prim_bounds(kp_ctx *ctx, const float *d_xyz, int64_t n, int32_t *d_bounds_enc)
+{
+    KP_PROFB(ctx, "bounds", (double)n * 12.0);
+    k_bounds_init<<<1, 32, 0, ctx->stream>>>(d_bounds_enc);
+    KP_LAUNCH_CHECK(ctx);
+    if (n > 0) {
+        unsigned nb = kp_blocks(n, 256 * 8);
+        unsigned cap = (unsigned)ctx->sm_count * 8;
+        if (nb > cap) nb = cap;
+        k_bounds<<<nb, 256, 0, ctx->stream>>>(d_xyz, n, d_bounds_enc);
+        KP_LAUNCH_CHECK(ctx);
+    }
+    return KP_OK;
+}
+
+static inline float kp_host_ord2f(int32_t i)
+{
+    int32_t b = i >= 0 ? i : i ^ 0x7fffffff;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+
+int kp_prim_bounds_fetch(kp_ctx *ctx, const float *d_xyz, int64_t n, float *h_bounds6, int64_t *h_nvalid)
+{
+    int32_t *enc = (int32_t *)ctx->d_scratch;
+    KP_TRY(kp_prim_bounds(ctx, d_xyz, n, enc));
+    KP_TRY(kp_fetch_scratch(ctx, 8 * sizeof(int32_t)));
+    const int32_t *h = (const int32_t *)ctx->h_scratch;
+    for (int c = 0; c < 6; ++c) h_bounds6[c] = kp_host_ord2f(h[c]);
+    if (h_nvalid) *h_nvalid = h[6];
+    return KP_OK;
+}
+
+// ========================================================= canonical sum ==
+namespace {
+// one warp per group of 1024 values: lane t adds x[t], x[t+32], ... in order, then the butterfly
+__global__ void __launch_bounds__(256) k_csum_level(const double *x, int64_t n, double *out, int64_t groups)
+{
+    int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= groups) return;
+    const int lane = threadIdx.x & 31;
+    int64_t lo = g * 1024;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+        int64_t i = lo + r * 32 + lane;
+        if (i < n) acc = __dadd_rn(acc, x[i]);
+    }
+    acc = kp_butterfly_sum(acc);
+    if (lane == 0) out[g] = acc;
+}
+__global__ void k_count_u8(const uint8_t *m, int64_t n, int32_t *total)
+{
+    int c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) c += m[i] != 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) c += __shfl_xor_sync(KP_FULL, c, s);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
+}
+}  // namespace
+
+int kp_prim_csum(kp_ctx *ctx, const double *d_x, int64_t n, double *d_tmp, double *d_out)
+{
+    if (n <= 0) {
+        KP_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(double), ctx->stream));
+        return KP_OK;
+    }
+    const double *cur = d_x;
+    int64_t cn = n;
+    double *nxt = d_tmp;
+    for (;;) {
+        int64_t groups = (cn + 1023) / 1024;
+        double *dst = groups == 1 ? d_out : nxt;
+        k_csum_level<<<kp_blocks(groups, 8), 256, 0, ctx->stream>>>(cur, cn, dst, groups);
+        KP_LAUNCH_CHECK(ctx);
+        if (groups == 1) break;
+        cur = dst;
+        cn = groups;
+        nxt = dst + groups;
+    }
+    return KP_OK;
+}
+
+int kp_prim_count_u8(kp_ctx *ctx, const uint8_t *d_mask, int64_t n, int32_t *d_total)
+{
+    KP_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(int32_t), ctx->stream));
+    if (n <= 0) return KP_OK;
+    unsigned nb = kp_blocks(n, 256 * 16);
+    unsigned cap = (unsigned)ctx->sm_count * 8;
+    if (nb > cap) nb = cap;
+    k_count_u8<<<nb, 256, 0, ctx->stream>>>(d_mask, n, d_total);
+    KP_LAUNCH_CHECK(ctx);
+    return KP_OK;
+}

@@ -1,0 +1,63 @@
+"""B200 counterpart of the reference's ``preprocessing/registration.py``.
+
+Same function names, argument order and defaults.  The voxel downsample, normal estimation and the
+whole point-to-plane ICP loop run on the GPU.  FPFH features, feature-matching global registration
+and coloured ICP are the "next" rows of SURVEY.md section 8f and raise ``NotImplementedError``.
+
+Roles, as in the reference: ``prepare_dataset`` makes the *sub* cloud the ICP source and the
+*master* cloud the target (``registration.py:25-26``), so the returned 4x4 maps sub coordinates
+into the master frame; ``execute_point_to_plane_registration`` swaps its local names before
+calling it (``registration.py:73-77``), which this module reproduces.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+from .. import geometry as _g
+from ..geometry import PointCloud
+
+
+def preprocess_point_cloud(pcd: PointCloud, voxel_size, normals_nn=30, fpfh_nn=100):
+    """voxel -> normals (hybrid search: radius 2*voxel, at most ``normals_nn``) (``registration.py:7-21``).
+
+    The second return value is the FPFH feature in the reference; it is computed lazily there too
+    (the ICP wrapper throws it away, ``registration.py:77``) and is ``None`` here.
+    """
+    down = pcd.voxel_down_sample(voxel_size)
+    down.estimate_normals(_g.KDTreeSearchParamHybrid(radius=voxel_size * 2, max_nn=normals_nn))
+    return down, None
+
+
+def prepare_dataset(pcd_master, pcd_sub, voxel_size, normals_nn=40, fpfh_nn=40):
+    source, target = copy.deepcopy(pcd_sub), copy.deepcopy(pcd_master)
+    source_down, source_fpfh = preprocess_point_cloud(source, voxel_size, normals_nn, fpfh_nn)
+    target_down, target_fpfh = preprocess_point_cloud(target, voxel_size, normals_nn, fpfh_nn)
+    return source, target, source_down, target_down, source_fpfh, target_fpfh
+
+
+def execute_global_registration(pcd_master, pcd_sub, voxel_size: int = 35, ransac_n_trials: int = 15) -> np.ndarray:
+    raise NotImplementedError("FPFH + feature-matching RANSAC global registration is a 'next' row "
+                              "(SURVEY.md section 8f, f3); pass an initial transformation to "
+                              "execute_point_to_plane_registration instead")
+
+
+def execute_point_to_plane_registration(pcd_master, pcd_sub, initial_transformation, voxel_size: int = 35,
+                                        threshold: float = 100, return_result: bool = False):
+    """Point-to-plane ICP refinement of ``initial_transformation`` (``registration.py:65-86``).
+
+    ``threshold`` is the literal 100 of ``registration.py:75`` exposed as a keyword (the reference
+    works in millimetres; BASELINE configs use metres).  Open3D's default criteria apply:
+    30 iterations, 1e-6 / 1e-6.
+    """
+    first, second = copy.deepcopy(pcd_master), copy.deepcopy(pcd_sub)
+    # the reference passes (master, sub) into prepare_dataset(pcd_master, pcd_sub): source <- sub, target <- master
+    _, _, source_down, target_down, _, _ = prepare_dataset(first, second, voxel_size)
+    result = _g.registration_icp(source_down, target_down, threshold, initial_transformation,
+                                 _g.TransformationEstimationPointToPlane())
+    return result if return_result else result.transformation
+
+
+def execute_colored_ICP_registration(pcd_master, pcd_sub, initial_transformation):
+    raise NotImplementedError("coloured ICP is a 'next' row (SURVEY.md section 8f, f4)")
