@@ -4,7 +4,8 @@
 NVCC      ?= nvcc
 ORACLE_CC ?= /usr/bin/gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v
+# -fmad=false: no FMA contraction anywhere, so decision arithmetic matches the oracle (gcc -ffp-contract=off)
+NVFLAGS   := $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v
 CSRC      := kinectpy_b200/csrc
 SRCS      := $(wildcard $(CSRC)/*.cu)
 OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))

@@ -139,11 +139,14 @@ int kp_grid_build(kp_ctx *ctx, const float *d_xyz, int64_t n, double cell, const
 int kp_grid_auto_cell(kp_ctx *ctx, const float *d_xyz, int64_t n, const float *h_bounds6, double target_per_cell,
                       double *cell_out);
 // cell edge for a k-nearest search on a cloud that was voxel-downsampled at `voxel`
-static inline double kp_knn_cell_from_voxel(double voxel, int k) { return voxel * 1.1 * sqrt((double)k / 3.14159265358979) ; }
+// (1.5 x the k-neighbour radius of an ideal 1-point-per-voxel surface: sensor clouds are sparser than the
+// voxel grid far from the camera; sweep in profiles/r01_c_knn_base_coarse_sweep.log)
+static inline double kp_knn_cell_from_voxel(double voxel, int k) { return voxel * 1.5 * sqrt((double)k / 3.14159265358979); }
 
 // internal forms used by the public API and by the frame pipeline (device pointers, async)
 int kp_knn_device(kp_ctx *ctx, const KpGrid &g, const float *d_queries, int64_t nq, int k, double radius,
-                  int32_t *d_idx, double *d_d2, int32_t *d_count, double *d_mean /*nullable: mean sqrt dist*/);
+                  int32_t *d_idx, double *d_d2, int32_t *d_count, double *d_mean /*nullable: mean sqrt dist*/,
+                  const float *d_xyz = nullptr /*cloud behind the grid: enables the coarse-level cascade*/);
 int kp_sor_device(kp_ctx *ctx, const float *d_xyz, int64_t n, int k, double ratio, double cell_hint,
                   const float *h_bounds6, uint8_t *d_keep, double *d_mean, double *h_stats, int64_t *h_kept);
 int kp_normals_device(kp_ctx *ctx, const float *d_xyz, int64_t n, double radius, int max_nn, const float *h_bounds6,

@@ -13,6 +13,7 @@
 // so the search stops as soon as the k-th distance is inside that radius; otherwise the next
 // shell of cells is probed (isolated outliers -- the points SOR exists to find -- take this path).
 #include <math.h>
+#include <stdlib.h>
 #include "kp_grid.cuh"
 
 KpGridDev kp_grid_dev(const KpGrid &g)
@@ -230,6 +231,9 @@ struct KnnParams {
     int32_t *idx; double *d2; int32_t *count; double *mean;
     const float *cloud; float *normals;
     int32_t *rcount;
+    const int32_t *qlist; const int32_t *qcount;   // visit only these query positions (rows of qpts)
+    uint8_t *strag_flags;                          // thread kernel: flags[q] = 1 for queries it could not certify
+    const float4 *qpts;                            // self-query source rows (level-0 cell-sorted array)
 };
 
 __device__ __forceinline__ bool kq_less(double d, int i, double td, int ti) { return d < td || (d == td && i < ti); }
@@ -396,148 +400,300 @@ __device__ void kq_smallest_eigvec(const double *cov, double *nrm)
     }
 }
 
+// Results of one query, written by ONE thread from its list sorted ascending by (d2, index)
+// (entry t at bd[t*stride], bi[t*stride]).  Sums run sequentially in that order -- the order Open3D's
+// std::accumulate sees (the KD-tree returns neighbours by ascending distance) and the oracle uses.
+__device__ void kq_finalize(const KnnParams &p, int64_t row, int cnt, const double *bd, const int *bi, int stride)
+{
+    if (p.mode == KQ_MODE_KNN) {
+        if (p.idx) for (int t = 0; t < p.k; ++t) p.idx[row * p.k + t] = t < cnt ? bi[t * stride] : -1;
+        if (p.d2) for (int t = 0; t < p.k; ++t) p.d2[row * p.k + t] = t < cnt ? bd[t * stride] : INFINITY;
+        if (p.count) p.count[row] = cnt;
+        if (p.mean) {
+            double acc = 0.0;
+            for (int t = 0; t < cnt; ++t) acc = __dadd_rn(acc, sqrt(bd[t * stride]));
+            p.mean[row] = cnt > 0 ? __ddiv_rn(acc, (double)cnt) : -1.0;
+        }
+        return;
+    }
+    // normals: covariance from cumulants over the neighbourhood, smallest eigenvector
+    double nr[3] = {0.0, 0.0, 1.0};
+    if (cnt >= 3) {
+        double sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int t = 0; t < cnt; ++t) {
+            int64_t j = bi[t * stride];
+            double x = (double)p.cloud[3 * j], y = (double)p.cloud[3 * j + 1], z = (double)p.cloud[3 * j + 2];
+            sm[0] += x; sm[1] += y; sm[2] += z;
+            sm[3] += x * x; sm[4] += x * y; sm[5] += x * z; sm[6] += y * y; sm[7] += y * z; sm[8] += z * z;
+        }
+        double inv = (double)cnt;
+        for (int c = 0; c < 9; ++c) sm[c] /= inv;
+        double cov[6] = {sm[3] - sm[0] * sm[0], sm[4] - sm[0] * sm[1], sm[5] - sm[0] * sm[2],
+                         sm[6] - sm[1] * sm[1], sm[7] - sm[1] * sm[2], sm[8] - sm[2] * sm[2]};
+        kq_smallest_eigvec(cov, nr);
+        if (nr[0] == 0.0 && nr[1] == 0.0 && nr[2] == 0.0) nr[2] = 1.0;
+    }
+    p.normals[3 * row] = (float)nr[0]; p.normals[3 * row + 1] = (float)nr[1]; p.normals[3 * row + 2] = (float)nr[2];
+}
+
+// ---- warp-per-query kernel: any k, ring expansion, linear-scan fallback.  Used for large k, for external
+// queries and for the stragglers the thread-per-query kernel hands over (qlist / qcount).
 __global__ void __launch_bounds__(KQ_WARPS * 32) k_knn(const __grid_constant__ KnnParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t q = (int64_t)blockIdx.x * KQ_WARPS + warp;
-    if (q >= p.nq) return;
     const KpGridDev &g = p.g;
+    const int64_t nq = p.qcount ? (int64_t)*p.qcount : p.nq;
+    for (int64_t w = (int64_t)blockIdx.x * KQ_WARPS + warp; w < nq; w += (int64_t)gridDim.x * KQ_WARPS) {
+        const int64_t q = p.qlist ? (int64_t)p.qlist[w] : w;
+        KqState s;
+        s.bd = reinterpret_cast<double *>(smem_raw) + (size_t)warp * p.cap;
+        s.bi = reinterpret_cast<int *>(reinterpret_cast<double *>(smem_raw) + (size_t)KQ_WARPS * p.cap) + (size_t)warp * p.cap;
+        s.n_buf = 0; s.k = p.k; s.cap = p.cap; s.lane = lane; s.rcount = 0;
+        s.tau_d = p.r2cap > 0 ? p.r2cap : INFINITY;
+        s.tau_i = p.r2cap > 0 ? (int)0x80000000 : 0x7fffffff;   // strict d2 < r2cap: equality never passes
 
-    KqState s;
-    s.bd = reinterpret_cast<double *>(smem_raw) + (size_t)warp * p.cap;
-    s.bi = reinterpret_cast<int *>(reinterpret_cast<double *>(smem_raw) + (size_t)KQ_WARPS * p.cap) + (size_t)warp * p.cap;
-    s.n_buf = 0; s.k = p.k; s.cap = p.cap; s.lane = lane; s.rcount = 0;
-    s.tau_d = p.r2cap > 0 ? p.r2cap : INFINITY;
-    s.tau_i = p.r2cap > 0 ? (int)0x80000000 : 0x7fffffff;   // strict d2 < r2cap: equality never passes
-
-    int64_t row;
-    if (p.queries) {
-        s.qx = (double)p.queries[3 * q]; s.qy = (double)p.queries[3 * q + 1]; s.qz = (double)p.queries[3 * q + 2];
-        row = q;
-    } else {
-        float4 me = __ldg(g.pts + q);
-        s.qx = (double)me.x; s.qy = (double)me.y; s.qz = (double)me.z;
-        row = __float_as_int(me.w);
-    }
-    const bool qnan = isnan(s.qx);
-    if (!qnan && g.dim[0] > 0) {
-        // Rings are centred on the in-grid cell nearest to the query.  For a query inside the grid that is
-        // its own cell; for an outside query, a grid point within distance rho of the query still lies
-        // within ceil(rho/cell) cells of the clamped cell on every axis, so the ring-r guarantee
-        // ("everything closer than r*cell has been seen") holds unchanged.
-        const int cx = min(max(kp_cell_coord(g, s.qx, 0), 0), g.dim[0] - 1);
-        const int cy = min(max(kp_cell_coord(g, s.qy, 1), 0), g.dim[1] - 1);
-        const int cz = min(max(kp_cell_coord(g, s.qz, 2), 0), g.dim[2] - 1);
-        // rings needed to cover the whole grid from this cell
-        int maxring = max(max(max(cx, g.dim[0] - 1 - cx), max(cy, g.dim[1] - 1 - cy)), max(cz, g.dim[2] - 1 - cz));
-        if (maxring < 1) maxring = 1;
-        // ---- ring 0+1: the 27-cell block, z-rows merged
-        {
-            int2 r = make_int2(0, 0);
-            if (lane < 27) r = kp_cell_range(g, cx + lane / 9 - 1, cy + (lane / 3) % 3 - 1, cz + lane % 3 - 1);
-            bool ne = r.y > r.x;
-            int a = ne ? r.x : 0x7fffffff, b = ne ? r.y : 0;
-            int a1 = __shfl_down_sync(KP_FULL, a, 1), b1 = __shfl_down_sync(KP_FULL, b, 1);
-            int a2 = __shfl_down_sync(KP_FULL, a, 2), b2 = __shfl_down_sync(KP_FULL, b, 2);
-            if (lane < 27 && lane % 3 == 0) { a = min(a, min(a1, a2)); b = max(b, max(b1, b2)); if (b == 0) a = 0; }
-            else { a = 0; b = 0; }
-            kq_scan_ranges(g, a, b, s, p.mode);
+        int64_t row;
+        if (p.queries) {
+            s.qx = (double)p.queries[3 * q]; s.qy = (double)p.queries[3 * q + 1]; s.qz = (double)p.queries[3 * q + 2];
+            row = q;
+        } else {
+            float4 me = __ldg(p.qpts + q);
+            s.qx = (double)me.x; s.qy = (double)me.y; s.qz = (double)me.z;
+            row = __float_as_int(me.w);
         }
-        int ring = 1;
-        if (p.mode != KQ_MODE_RADIUS) {
-            for (;;) {
-                kq_truncate(s);
-                double safe = (double)ring * g.cell * (1.0 - 1.0 / 1048576.0);
-                double s2 = safe * safe;
-                if (s.n_buf == s.k && s.tau_d <= s2) break;
-                if (p.r2cap > 0 && p.r2cap <= s2) break;
-                if (ring >= maxring) break;
-                ++ring;
-                {
-                    // A shell this large costs more probes than the cloud has points: finish with one exact
-                    // linear pass over the sorted array instead (bounds the work of far-away stragglers).
-                    const long long w3 = 2LL * ring + 1;
-                    if (w3 * w3 * w3 > (long long)g.npts) {
-                        s.n_buf = 0;
-                        s.tau_d = p.r2cap > 0 ? p.r2cap : INFINITY;
-                        s.tau_i = p.r2cap > 0 ? (int)0x80000000 : 0x7fffffff;
-                        kq_scan_ranges(g, lane == 0 ? 0 : 0, lane == 0 ? g.npts : 0, s, p.mode);
-                        kq_truncate(s);
-                        break;
-                    }
-                }
-                // ---- shell `ring`: two full slabs dz = +-ring, then the perimeter of every layer in between
-                const long long w = 2LL * ring + 1;
-                const long long slab = w * w, per = 4 * (w - 1);
-                const long long ncell = 2 * slab + (w - 2) * per;
-                for (long long e0 = 0; e0 < ncell; e0 += 32) {
-                    long long e = e0 + lane;
-                    int2 r = make_int2(0, 0);
-                    if (e < ncell) {
-                        int dx, dy, dz;
-                        if (e < 2 * slab) {
-                            int sl = (int)(e / slab);
-                            long long rem = e % slab;
-                            dx = (int)(rem / w) - ring; dy = (int)(rem % w) - ring; dz = sl ? ring : -ring;
-                        } else {
-                            long long e2 = e - 2 * slab;
-                            int layer = (int)(e2 / per), pi = (int)(e2 % per);
-                            dz = -ring + 1 + layer;
-                            int side = pi / (int)(w - 1), t = pi % (int)(w - 1);
-                            if (side == 0) { dx = -ring + t; dy = -ring; }
-                            else if (side == 1) { dx = ring; dy = -ring + t; }
-                            else if (side == 2) { dx = ring - t; dy = ring; }
-                            else { dx = -ring; dy = ring - t; }
+        const bool qnan = isnan(s.qx);
+        if (!qnan && g.dim[0] > 0) {
+            // Rings are centred on the in-grid cell nearest to the query.  For a query inside the grid that is
+            // its own cell; for an outside query, a grid point within distance rho of the query still lies
+            // within ceil(rho/cell) cells of the clamped cell on every axis, so the ring-r guarantee
+            // ("everything closer than r*cell has been seen") holds unchanged.
+            const int cx = min(max(kp_cell_coord(g, s.qx, 0), 0), g.dim[0] - 1);
+            const int cy = min(max(kp_cell_coord(g, s.qy, 1), 0), g.dim[1] - 1);
+            const int cz = min(max(kp_cell_coord(g, s.qz, 2), 0), g.dim[2] - 1);
+            // rings needed to cover the whole grid from this cell
+            int maxring = max(max(max(cx, g.dim[0] - 1 - cx), max(cy, g.dim[1] - 1 - cy)), max(cz, g.dim[2] - 1 - cz));
+            if (maxring < 1) maxring = 1;
+            // ---- ring 0+1: the 27-cell block, z-rows merged
+            {
+                int2 r = make_int2(0, 0);
+                if (lane < 27) r = kp_cell_range(g, cx + lane / 9 - 1, cy + (lane / 3) % 3 - 1, cz + lane % 3 - 1);
+                bool ne = r.y > r.x;
+                int a = ne ? r.x : 0x7fffffff, b = ne ? r.y : 0;
+                int a1 = __shfl_down_sync(KP_FULL, a, 1), b1 = __shfl_down_sync(KP_FULL, b, 1);
+                int a2 = __shfl_down_sync(KP_FULL, a, 2), b2 = __shfl_down_sync(KP_FULL, b, 2);
+                if (lane < 27 && lane % 3 == 0) { a = min(a, min(a1, a2)); b = max(b, max(b1, b2)); if (b == 0) a = 0; }
+                else { a = 0; b = 0; }
+                kq_scan_ranges(g, a, b, s, p.mode);
+            }
+            int ring = 1;
+            if (p.mode != KQ_MODE_RADIUS) {
+                for (;;) {
+                    kq_truncate(s);
+                    double safe = (double)ring * g.cell * (1.0 - 1.0 / 1048576.0);
+                    double s2 = safe * safe;
+                    if (s.n_buf == s.k && s.tau_d <= s2) break;
+                    if (p.r2cap > 0 && p.r2cap <= s2) break;
+                    if (ring >= maxring) break;
+                    ++ring;
+                    {
+                        // A shell this large costs more probes than the cloud has points: finish with one exact
+                        // linear pass over the sorted array instead (bounds the work of far-away stragglers).
+                        const long long w3 = 2LL * ring + 1;
+                        if (w3 * w3 * w3 > (long long)g.npts) {
+                            s.n_buf = 0;
+                            s.tau_d = p.r2cap > 0 ? p.r2cap : INFINITY;
+                            s.tau_i = p.r2cap > 0 ? (int)0x80000000 : 0x7fffffff;
+                            kq_scan_ranges(g, 0, lane == 0 ? g.npts : 0, s, p.mode);
+                            kq_truncate(s);
+                            break;
                         }
-                        r = kp_cell_range(g, cx + dx, cy + dy, cz + dz);
                     }
-                    kq_scan_ranges(g, r.x, r.y, s, p.mode);
+                    // ---- shell `ring`: two full slabs dz = +-ring, then the perimeter of every layer in between
+                    const long long sw = 2LL * ring + 1;
+                    const long long slab = sw * sw, per = 4 * (sw - 1);
+                    const long long ncell = 2 * slab + (sw - 2) * per;
+                    for (long long e0 = 0; e0 < ncell; e0 += 32) {
+                        long long e = e0 + lane;
+                        int2 r = make_int2(0, 0);
+                        if (e < ncell) {
+                            int dx, dy, dz;
+                            if (e < 2 * slab) {
+                                int sl = (int)(e / slab);
+                                long long rem = e % slab;
+                                dx = (int)(rem / sw) - ring; dy = (int)(rem % sw) - ring; dz = sl ? ring : -ring;
+                            } else {
+                                long long e2 = e - 2 * slab;
+                                int layer = (int)(e2 / per), pi = (int)(e2 % per);
+                                dz = -ring + 1 + layer;
+                                int side = pi / (int)(sw - 1), t = pi % (int)(sw - 1);
+                                if (side == 0) { dx = -ring + t; dy = -ring; }
+                                else if (side == 1) { dx = ring; dy = -ring + t; }
+                                else if (side == 2) { dx = ring - t; dy = ring; }
+                                else { dx = -ring; dy = ring - t; }
+                            }
+                            r = kp_cell_range(g, cx + dx, cy + dy, cz + dz);
+                        }
+                        kq_scan_ranges(g, r.x, r.y, s, p.mode);
+                    }
                 }
             }
         }
+        if (p.mode == KQ_MODE_RADIUS) {
+            if (lane == 0) p.rcount[row] = s.rcount;
+        } else {
+            __syncwarp();
+            if (lane == 0) kq_finalize(p, row, qnan ? 0 : s.n_buf, s.bd, s.bi, 1);
+        }
+        __syncwarp();
     }
+}
 
-    if (p.mode == KQ_MODE_RADIUS) {
-        if (lane == 0) p.rcount[row] = s.rcount;
-        return;
-    }
-    const int cnt = qnan ? 0 : s.n_buf;
-    if (p.mode == KQ_MODE_KNN) {
-        if (p.idx) for (int t = lane; t < p.k; t += 32) p.idx[row * p.k + t] = t < cnt ? s.bi[t] : -1;
-        if (p.d2) for (int t = lane; t < p.k; t += 32) p.d2[row * p.k + t] = t < cnt ? s.bd[t] : INFINITY;
-        if (p.count && lane == 0) p.count[row] = cnt;
-        if (p.mean) {
-            // mean of sqrt(d2) over the neighbours, canonical 32-lane sum (oracle: kpo_csum32)
-            double acc = 0.0;
-            for (int t = lane; t < cnt; t += 32) acc = __dadd_rn(acc, sqrt(s.bd[t]));
-            acc = kp_butterfly_sum(acc);
-            if (lane == 0) p.mean[row] = cnt > 0 ? __ddiv_rn(acc, (double)cnt) : -1.0;
-        }
-        return;
-    }
-    // ---- normals: covariance from cumulants over the neighbourhood, smallest eigenvector
-    double sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = lane; t < cnt; t += 32) {
-        int64_t j = s.bi[t];
-        double x = (double)p.cloud[3 * j], y = (double)p.cloud[3 * j + 1], z = (double)p.cloud[3 * j + 2];
-        sm[0] += x; sm[1] += y; sm[2] += z;
-        sm[3] += x * x; sm[4] += x * y; sm[5] += x * z; sm[6] += y * y; sm[7] += y * z; sm[8] += z * z;
-    }
+// ---- thread-per-query kernel (the fast path, k <= TQ_KMAX, the cloud queries itself).
+// Queries are taken in cell-sorted order, so the lanes of a warp sit in the same or adjacent cells and
+// walk (almost) the same candidate ranges: their 16-byte candidate loads hit the same L1 lines, which is
+// the shared staging of the cell neighbourhood.  Each thread keeps a max-heap of its k best (d2, index)
+// pairs in shared memory, laid out [slot][thread] so that any slot pattern is bank-conflict free.
+// Rows of cells whose nearest face is already farther than the current k-th distance are skipped.
+// A query whose k-th distance is not certified by the 27-cell block (isolated points: what SOR is
+// looking for) is appended to a straggler list and finished by the warp kernel above.
+constexpr int TQ_THREADS = 128;
+constexpr int TQ_KMAX = 64;
+
+__device__ __forceinline__ bool tq_greater(double d, int i, double e, int j) { return d > e || (d == e && i > j); }
+
+__global__ void __launch_bounds__(TQ_THREADS) k_knn_tq(const __grid_constant__ KnnParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const KpGridDev &g = p.g;
+    const int tid = threadIdx.x;
+    const int64_t w = (int64_t)blockIdx.x * TQ_THREADS + tid;
+    if (w >= p.nq) return;
+    const int64_t q = p.qlist ? (int64_t)p.qlist[w] : w;
+    double *hd = reinterpret_cast<double *>(smem_raw) + tid;                                   // hd[slot * TQ_THREADS]
+    int *hi = reinterpret_cast<int *>(reinterpret_cast<double *>(smem_raw) + (size_t)p.k * TQ_THREADS) + tid;
+    const int k = p.k;
+    const float4 me = __ldg(p.qpts + q);
+    const int64_t row = __float_as_int(me.w);
+    const double qx = (double)me.x, qy = (double)me.y, qz = (double)me.z;
+    if (isnan(qx)) { kq_finalize(p, row, 0, hd, hi, TQ_THREADS); return; }
+    const int cx = kp_cell_coord(g, qx, 0), cy = kp_cell_coord(g, qy, 1), cz = kp_cell_coord(g, qz, 2);
+    // distance from the query to the faces of its own cell, per axis (low, high), slightly shrunk so
+    // that rounding in the cell assignment can never make a pruned row hold a closer point
+    const double shrink = 1.0 - 1.0 / 1048576.0;
+    double glo[3], ghi[3];
+    {
+        const double qq[3] = {qx, qy, qz};
+        const int cc[3] = {cx, cy, cz};
 #pragma unroll
-    for (int c = 0; c < 9; ++c) sm[c] = kp_butterfly_sum(sm[c]);
-    if (lane == 0) {
-        double nr[3] = {0.0, 0.0, 1.0};
-        if (cnt >= 3) {
-            double inv = (double)cnt;
-            for (int c = 0; c < 9; ++c) sm[c] /= inv;
-            double cov[6] = {sm[3] - sm[0] * sm[0], sm[4] - sm[0] * sm[1], sm[5] - sm[0] * sm[2],
-                             sm[6] - sm[1] * sm[1], sm[7] - sm[1] * sm[2], sm[8] - sm[2] * sm[2]};
-            kq_smallest_eigvec(cov, nr);
-            if (nr[0] == 0.0 && nr[1] == 0.0 && nr[2] == 0.0) nr[2] = 1.0;
+        for (int c = 0; c < 3; ++c) {
+            double f = (qq[c] - g.org[c]) * g.inv_cell - (double)cc[c];
+            f = fmin(fmax(f, 0.0), 1.0);
+            glo[c] = f * g.cell * shrink;
+            ghi[c] = (1.0 - f) * g.cell * shrink;
         }
-        p.normals[3 * row] = (float)nr[0]; p.normals[3 * row + 1] = (float)nr[1]; p.normals[3 * row + 2] = (float)nr[2];
     }
+    int n = 0;
+    const bool capped = p.r2cap > 0;
+    // the heap's root (current k-th best) is mirrored in registers: the common "reject" test touches no memory
+    double topd = INFINITY;
+    int topi = 0x7fffffff;
+    auto offer = [&](double d, int id) {
+        if (capped && !(d < p.r2cap)) return;
+        if (n < k) {
+            int pos = n++;   // push: sift up
+            while (pos > 0) {
+                int par = (pos - 1) >> 1;
+                double pd = hd[par * TQ_THREADS]; int pi = hi[par * TQ_THREADS];
+                if (!tq_greater(d, id, pd, pi)) break;
+                hd[pos * TQ_THREADS] = pd; hi[pos * TQ_THREADS] = pi;
+                pos = par;
+            }
+            hd[pos * TQ_THREADS] = d; hi[pos * TQ_THREADS] = id;
+            if (n == k) { topd = hd[0]; topi = hi[0]; }
+        } else if (tq_greater(topd, topi, d, id)) {
+            int pos = 0;     // replace the current worst: sift down
+            for (;;) {
+                int ch = 2 * pos + 1;
+                if (ch >= k) break;
+                double cd = hd[ch * TQ_THREADS]; int ci = hi[ch * TQ_THREADS];
+                if (ch + 1 < k) {
+                    double ed = hd[(ch + 1) * TQ_THREADS]; int ei = hi[(ch + 1) * TQ_THREADS];
+                    if (tq_greater(ed, ei, cd, ci)) { cd = ed; ci = ei; ++ch; }
+                }
+                if (!tq_greater(cd, ci, d, id)) break;
+                hd[pos * TQ_THREADS] = cd; hi[pos * TQ_THREADS] = ci;
+                pos = ch;
+            }
+            hd[pos * TQ_THREADS] = d; hi[pos * TQ_THREADS] = id;
+            topd = hd[0]; topi = hi[0];
+        }
+    };
+    // rows ordered so the query's own row comes first (tightens the k-th distance early)
+    const int order[9] = {4, 1, 3, 5, 7, 0, 2, 6, 8};
+    for (int oi = 0; oi < 9; ++oi) {
+        const int dx = order[oi] / 3 - 1, dy = order[oi] % 3 - 1;
+        if (n == k || capped) {
+            const double gx = dx < 0 ? glo[0] : (dx > 0 ? ghi[0] : 0.0), gy = dy < 0 ? glo[1] : (dy > 0 ? ghi[1] : 0.0);
+            const double m2 = gx * gx + gy * gy;
+            if (n == k && m2 > topd) continue;
+            if (capped && m2 >= p.r2cap) continue;
+        }
+        int a = 0x7fffffff, b = 0;
+#pragma unroll
+        for (int dz = -1; dz <= 1; ++dz) {
+            int2 r = kp_cell_range(g, cx + dx, cy + dy, cz + dz);
+            if (r.y > r.x) { a = min(a, r.x); b = max(b, r.y); }
+        }
+        // four candidates per trip: the loads and the four distance chains are independent, only the
+        // offers are sequential (keeps the FP64 pipe busy at the low occupancy a per-thread heap allows)
+        for (int t = a; t < b; t += 4) {
+            const int m = b - t;
+            const float4 c0 = __ldg(g.pts + t);
+            const float4 c1 = __ldg(g.pts + (m > 1 ? t + 1 : t));
+            const float4 c2 = __ldg(g.pts + (m > 2 ? t + 2 : t));
+            const float4 c3 = __ldg(g.pts + (m > 3 ? t + 3 : t));
+            const double d0 = kp_d2(qx, qy, qz, (double)c0.x, (double)c0.y, (double)c0.z);
+            const double d1 = kp_d2(qx, qy, qz, (double)c1.x, (double)c1.y, (double)c1.z);
+            const double d2 = kp_d2(qx, qy, qz, (double)c2.x, (double)c2.y, (double)c2.z);
+            const double d3 = kp_d2(qx, qy, qz, (double)c3.x, (double)c3.y, (double)c3.z);
+            offer(d0, __float_as_int(c0.w));
+            if (m > 1) offer(d1, __float_as_int(c1.w));
+            if (m > 2) offer(d2, __float_as_int(c2.w));
+            if (m > 3) offer(d3, __float_as_int(c3.w));
+        }
+    }
+    // certificate: every point closer than (cell + distance to the nearest face of the own cell) was seen
+    if (!capped || p.r2cap > g.cell * g.cell * shrink * shrink) {
+        double mg = fmin(fmin(fmin(glo[0], ghi[0]), fmin(glo[1], ghi[1])), fmin(glo[2], ghi[2]));
+        double safe = g.cell * shrink + mg;
+        double s2 = safe * safe;
+        bool exact = (n == k && topd <= s2) || (capped && p.r2cap <= s2);
+        if (!exact) {
+            p.strag_flags[q] = 1;   // flag, not append: the list is compacted in query order so that the
+            return;                 // next level's warps again hold spatial neighbours
+        }
+    }
+    // heapsort in place -> ascending (d2, index)
+    for (int end = n - 1; end > 0; --end) {
+        const double d = hd[end * TQ_THREADS]; const int id = hi[end * TQ_THREADS];
+        hd[end * TQ_THREADS] = hd[0]; hi[end * TQ_THREADS] = hi[0];
+        int pos = 0;
+        for (;;) {
+            int ch = 2 * pos + 1;
+            if (ch >= end) break;
+            double cd = hd[ch * TQ_THREADS]; int ci = hi[ch * TQ_THREADS];
+            if (ch + 1 < end) {
+                double ed = hd[(ch + 1) * TQ_THREADS]; int ei = hi[(ch + 1) * TQ_THREADS];
+                if (tq_greater(ed, ei, cd, ci)) { cd = ed; ci = ei; ++ch; }
+            }
+            if (!tq_greater(cd, ci, d, id)) break;
+            hd[pos * TQ_THREADS] = cd; hi[pos * TQ_THREADS] = ci;
+            pos = ch;
+        }
+        hd[pos * TQ_THREADS] = d; hi[pos * TQ_THREADS] = id;
+    }
+    kq_finalize(p, row, n, hd, hi, TQ_THREADS);
 }
 
 int next_pow2(int v)
@@ -547,21 +703,89 @@ int next_pow2(int v)
     return p;
 }
 
-int knn_launch(kp_ctx *ctx, KnnParams &p, const char *name)
+int knn_launch_warp(kp_ctx *ctx, KnnParams &p, int64_t grid_queries)
+{
+    p.cap = next_pow2(p.k + 32);
+    if (p.cap < 64) p.cap = 64;
+    size_t smem = (size_t)KQ_WARPS * p.cap * (sizeof(double) + sizeof(int));
+    if (smem > 200 * 1024) return kp_set_err(ctx, KP_E_ARG, "k = %d neighbours is too many for the per-warp buffer", p.k);
+    if (smem > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (grid_queries + KQ_WARPS - 1) / KQ_WARPS;
+    int64_t cap_blocks = (int64_t)ctx->sm_count * 32;
+    if (p.qlist && blocks > cap_blocks) blocks = cap_blocks;     // persistent loop over the straggler list
+    if (blocks < 1) blocks = 1;
+    k_knn<<<(unsigned)blocks, KQ_WARPS * 32, smem, ctx->stream>>>(p);
+    KP_LAUNCH_CHECK(ctx);
+    return KP_OK;
+}
+
+// d_xyz: the cloud the grid was built from (needed to build the coarser cascade levels; may be NULL)
+int knn_launch(kp_ctx *ctx, KnnParams &p, const char *name, const float *d_xyz = nullptr)
 {
     if (p.nq <= 0) return KP_OK;
     // compulsory HBM traffic: the cell-sorted float4 array once + the per-query outputs
     double out_b = p.mode == KQ_MODE_RADIUS ? 4.0 : p.mode == KQ_MODE_NORMALS ? 12.0 + 12.0
                    : (p.idx ? 4.0 * p.k : 0.0) + (p.d2 ? 8.0 * p.k : 0.0) + (p.count ? 4.0 : 0.0) + (p.mean ? 8.0 : 0.0);
     KP_PROFB(ctx, name, (double)p.g.npts * 16.0 + (double)p.nq * (out_b + (p.queries ? 12.0 : 0.0)));
-    p.cap = next_pow2(p.k + 32);
-    if (p.cap < 64) p.cap = 64;
-    size_t smem = (size_t)KQ_WARPS * p.cap * (sizeof(double) + sizeof(int));
-    if (smem > 200 * 1024) return kp_set_err(ctx, KP_E_ARG, "k = %d neighbours is too many for the per-warp buffer", p.k);
-    if (smem > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn<<<kp_blocks(p.nq, KQ_WARPS), KQ_WARPS * 32, smem, ctx->stream>>>(p);
-    KP_LAUNCH_CHECK(ctx);
-    return KP_OK;
+    p.qlist = nullptr; p.qcount = nullptr; p.strag_flags = nullptr;
+    p.qpts = p.g.pts;
+    const bool fast = !p.queries && p.mode != KQ_MODE_RADIUS && p.k <= TQ_KMAX;
+    if (!fast) return knn_launch_warp(ctx, p, p.nq);
+    const KpGridDev g0 = p.g;
+    const int64_t nq0 = p.nq;
+    int32_t *listA, *counts;
+    uint8_t *flags;
+    KP_TRY(kp_ws(ctx, (size_t)nq0, &listA));
+    KP_TRY(kp_ws(ctx, (size_t)nq0, &flags));
+    KP_TRY(kp_ws(ctx, 8, &counts));
+    KP_CUDA(ctx, cudaMemsetAsync(counts, 0, 8 * sizeof(int32_t), ctx->stream));
+    KP_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)nq0, ctx->stream));
+    size_t smem = (size_t)p.k * TQ_THREADS * (sizeof(double) + sizeof(int));
+    if (smem > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_tq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // level 0: every query against the caller's grid
+    p.strag_flags = flags;
+    {
+        KP_PROF(ctx, "knn_level0");
+        k_knn_tq<<<kp_blocks(nq0, TQ_THREADS), TQ_THREADS, smem, ctx->stream>>>(p);
+        KP_LAUNCH_CHECK(ctx);
+    }
+    // A radius-capped search on a grid whose cell covers the radius is always certified: nothing to hand over.
+    const double shrink = 1.0 - 1.0 / 1048576.0;   // same test as the kernel's certificate
+    const bool always_exact = p.r2cap > 0 && !(p.r2cap > g0.cell * g0.cell * shrink * shrink);
+    if (always_exact) return KP_OK;
+    // Queries the 27-cell block could not certify: flying pixels and other isolated points (exactly what SOR is
+    // looking for) plus the sparsest fringes of the cloud.  Their k-th neighbour can be tens of cells away, so
+    // they are finished by the ring-expanding warp kernel on a much COARSER grid (few rings, long contiguous
+    // candidate runs that a warp streams 32 at a time).  The list is compacted in query order.
+    // (sweep in profiles/r01_c_knn_base_coarse_sweep.log: a 4x coarser grid halves the straggler pass for
+    // k = 20; for k = 50 the per-warp buffer sorts dominate and the level-0 grid is as good)
+    const double coarse_mult = getenv("KP_KNN_COARSE_MULT") ? atof(getenv("KP_KNN_COARSE_MULT")) : (p.k <= 32 ? 4.0 : 1.0);
+    KP_TRY(kp_prim_compact_mask(ctx, nq0, flags, 0, nullptr, nullptr, listA, counts));
+    KP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, counts, sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    KP_TRY(kp_fetch_scratch(ctx, sizeof(int32_t)));
+    const int32_t n_strag = *(int32_t *)ctx->h_scratch;
+    if (getenv("KP_DEBUG_KNN"))
+        fprintf(stderr, "[kp knn] %s k=%d n=%lld cell=%g uncertified=%d\n", name, p.k, (long long)nq0, g0.cell, n_strag);
+    if (n_strag <= 0) return KP_OK;
+    p.g = g0;
+    if (d_xyz && coarse_mult > 1.0) {
+        float b6[6];
+        for (int c = 0; c < 3; ++c) {
+            b6[c] = (float)g0.org[c];
+            b6[3 + c] = (float)(g0.org[c] + g0.cell * (double)g0.dim[c]);
+        }
+        KpGrid gl;
+        KP_TRY(kp_grid_build(ctx, d_xyz, g0.npts, g0.cell * coarse_mult, b6, &gl));
+        p.g = kp_grid_dev(gl);
+    }
+    p.qpts = g0.pts;
+    p.qlist = listA;
+    p.qcount = counts;
+    p.nq = nq0;
+    {
+        KP_PROF(ctx, "knn_stragglers");
+        return knn_launch_warp(ctx, p, n_strag);
+    }
 }
 
 // SOR statistics: the two canonical sums run on transformed copies of the mean array
@@ -595,7 +819,7 @@ __global__ void k_radius_mask(const int32_t *cnt, int64_t n, int nb, uint8_t *ke
 }  // namespace
 
 int kp_knn_device(kp_ctx *ctx, const KpGrid &g, const float *d_queries, int64_t nq, int k, double radius, int32_t *d_idx,
-                  double *d_d2, int32_t *d_count, double *d_mean)
+                  double *d_d2, int32_t *d_count, double *d_mean, const float *d_xyz)
 {
     KnnParams p;
     p.g = kp_grid_dev(g);
@@ -603,7 +827,7 @@ int kp_knn_device(kp_ctx *ctx, const KpGrid &g, const float *d_queries, int64_t 
     p.r2cap = radius > 0 ? radius * radius : 0.0;
     p.idx = d_idx; p.d2 = d_d2; p.count = d_count; p.mean = d_mean;
     p.cloud = nullptr; p.normals = nullptr; p.rcount = nullptr;
-    return knn_launch(ctx, p, "knn");
+    return knn_launch(ctx, p, "knn", d_xyz);
 }
 
 int kp_sor_device(kp_ctx *ctx, const float *d_xyz, int64_t n, int k, double ratio, double cell_hint,
@@ -637,7 +861,7 @@ int kp_sor_device(kp_ctx *ctx, const float *d_xyz, int64_t n, int k, double rati
         p.queries = nullptr; p.nq = n; p.k = k; p.mode = KQ_MODE_KNN; p.r2cap = 0.0;
         p.idx = nullptr; p.d2 = nullptr; p.count = nullptr; p.mean = mean;
         p.cloud = nullptr; p.normals = nullptr; p.rcount = nullptr;
-        KP_TRY(knn_launch(ctx, p, "sor_knn"));
+        KP_TRY(knn_launch(ctx, p, "sor_knn", d_xyz));
     }
     KP_PROFB(ctx, "sor_stats", (double)n * (7.0 * 8.0 + 2.0));
     // NaN points never get a neighbour list: they count as "not computed" (mean = -1), like upstream's
@@ -697,7 +921,7 @@ int kp_knn(kp_ctx *ctx, const float *d_xyz, int64_t n, const float *d_queries, i
     }
     KpGrid g;
     KP_TRY(kp_grid_build(ctx, d_xyz, n, cell, nullptr, &g));
-    return kp_knn_device(ctx, g, d_queries, nq, k, radius, d_idx, d_d2, d_count, nullptr);
+    return kp_knn_device(ctx, g, d_queries, nq, k, radius, d_idx, d_d2, d_count, nullptr, d_xyz);
 }
 
 int kp_sor_mask(kp_ctx *ctx, const float *d_xyz, int64_t n, int nb_neighbors, double std_ratio, double cell_hint,

@@ -108,8 +108,25 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(const __grid_constant_
         const int cx = kp_cell_coord(g, sx, 0), cy = kp_cell_coord(g, sy, 1), cz = kp_cell_coord(g, sz, 2);
         double bd = INFINITY;
         int bi = -1, bpos = -1;
-        for (int dx = -1; dx <= 1; ++dx)
-            for (int dy = -1; dy <= 1; ++dy) {
+        // distance to the faces of the own cell (x, y), shrunk a hair so rounding in the cell assignment can
+        // never hide a closer point: a row of cells farther than the best match so far is skipped
+        double glo[2], ghi[2];
+        {
+            const double shrink = 1.0 - 1.0 / 1048576.0;
+            double fx = fmin(fmax((sx - g.org[0]) * g.inv_cell - (double)cx, 0.0), 1.0);
+            double fy = fmin(fmax((sy - g.org[1]) * g.inv_cell - (double)cy, 0.0), 1.0);
+            glo[0] = fx * g.cell * shrink; ghi[0] = (1.0 - fx) * g.cell * shrink;
+            glo[1] = fy * g.cell * shrink; ghi[1] = (1.0 - fy) * g.cell * shrink;
+        }
+        const int order[9] = {4, 1, 3, 5, 7, 0, 2, 6, 8};   // own row first
+        for (int oi = 0; oi < 9; ++oi) {
+            const int dx = order[oi] / 3 - 1, dy = order[oi] % 3 - 1;
+            {
+                const double gx = dx < 0 ? glo[0] : (dx > 0 ? ghi[0] : 0.0), gy = dy < 0 ? glo[1] : (dy > 0 ? ghi[1] : 0.0);
+                const double m2 = gx * gx + gy * gy;
+                if (m2 >= p.r2 || m2 > bd) continue;
+            }
+            {
                 int a = 0x7fffffff, b = 0;
 #pragma unroll
                 for (int dz = -1; dz <= 1; ++dz) {
@@ -123,6 +140,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(const __grid_constant_
                     if (d2 < p.r2 && (d2 < bd || (d2 == bd && id < bi))) { bd = d2; bi = id; bpos = t; }
                 }
             }
+        }
         if (bi < 0) continue;
         float4 q = __ldg(g.pts + bpos);
         const double ex = sx - (double)q.x, ey = sy - (double)q.y, ez = sz - (double)q.z;

@@ -193,7 +193,7 @@ int kp_prim_run_starts_u32(kp_ctx *ctx, int64_t n, const uint32_t *d_keys, int32
 // ============================================================ radix sort ==
 // Stable LSD sort, 8 bits per pass, three kernels per pass:
 //   hist   : per-tile digit histogram           -> g_hist[digit][tile]
-//   scan   : exclusive scan over (digit, tile)  -> g_hist in place + g_base[digit]
+//   scan   : per-digit exclusive scan over tiles (one block per digit) -> g_hist in place + g_tot[digit]
 //   scatter: per-warp stable ranking with __match_any_sync, then direct scatter
 // Tile = 256 threads x RS_ITEMS keys; warp w owns a contiguous slab of RS_ITEMS*32 keys so the
 // order inside a tile is (warp, item, lane) = input order.
@@ -219,42 +219,39 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K *keys, int64_t n
     g_hist[(int64_t)threadIdx.x * nb + blockIdx.x] = hist[threadIdx.x];
 }
 
-// single block of 1024 threads (32 warps x 8 digits each)
-__global__ void __launch_bounds__(1024) k_rs_scan(int32_t *g_hist, int nb, int32_t *g_base)
+// one block per digit: exclusive scan of that digit's per-tile counts (row of g_hist), total to g_tot[digit]
+__global__ void __launch_bounds__(256) k_rs_scan_rows(int32_t *g_hist, int nb, int32_t *g_tot)
 {
-    __shared__ int tot[256];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int dd = 0; dd < 8; ++dd) {
-        int d = w * 8 + dd;
-        int32_t *row = g_hist + (int64_t)d * nb;
-        int carry = 0;
-        for (int base = 0; base < nb; base += 32) {
-            int i = base + lane;
-            int x = i < nb ? row[i] : 0;
-            int incl = x;
+    __shared__ int warp_tot[8];
+    const int d = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int32_t *row = g_hist + (int64_t)d * nb;
+    const int seg = (nb + 255) / 256;
+    const int lo = min(tid * seg, nb), hi = min(lo + seg, nb);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += row[i];
+    int incl = sum;
 #pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                int y = __shfl_up_sync(KP_FULL, incl, s);
-                if (lane >= s) incl += y;
-            }
-            if (i < nb) row[i] = carry + incl - x;
-            carry += __shfl_sync(KP_FULL, incl, 31);
-        }
-        if (lane == 0) tot[d] = carry;
+    for (int s = 1; s < 32; s <<= 1) {
+        int y = __shfl_up_sync(KP_FULL, incl, s);
+        if (lane >= s) incl += y;
     }
+    if (lane == 31) warp_tot[w] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int s = 0;
-        for (int d = 0; d < 256; ++d) { g_base[d] = s; s += tot[d]; }
-    }
+    int woff = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) woff += ww < w ? warp_tot[ww] : 0;
+    int run = woff + incl - sum;
+    for (int i = lo; i < hi; ++i) { int c = row[i]; row[i] = run; run += c; }
+    if (tid == 255) g_tot[d] = run;
 }
 
 template <class K>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K *keys_in, const int32_t *vals_in, K *keys_out,
                                                            int32_t *vals_out, int64_t n, int shift,
-                                                           const int32_t *g_hist, const int32_t *g_base, int nb)
+                                                           const int32_t *g_hist, const int32_t *g_tot, int nb)
 {
     __shared__ int cnt[RS_WARPS][256];
+    __shared__ int dig_wtot[RS_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int e = threadIdx.x; e < RS_WARPS * 256; e += RS_THREADS) (&cnt[0][0])[e] = 0;
     __syncthreads();
@@ -285,7 +282,19 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K *keys_in, con
     __syncthreads();
     {
         int d = threadIdx.x;   // 256 threads <-> 256 digits
-        int off = g_base[d] + g_hist[(int64_t)d * nb + blockIdx.x];
+        // global base of digit d = exclusive scan over the 256 digit totals (block scan, recomputed per tile)
+        int tot = g_tot[d], incl = tot;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            int y = __shfl_up_sync(KP_FULL, incl, s);
+            if (lane >= s) incl += y;
+        }
+        if (lane == 31) dig_wtot[w] = incl;
+        __syncthreads();
+        int base = incl - tot;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) base += ww < w ? dig_wtot[ww] : 0;
+        int off = base + g_hist[(int64_t)d * nb + blockIdx.x];
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ++ww) { int c = cnt[ww][d]; cnt[ww][d] = off; off += c; }
     }
@@ -323,7 +332,7 @@ int sort_pairs(kp_ctx *ctx, int64_t n, int bits, K *d_keys, K *d_keys_tmp, int32
         int shift = 8 * p;
         k_rs_hist<K><<<nb, RS_THREADS, 0, ctx->stream>>>(kin, n, shift, g_hist, nb);
         KP_LAUNCH_CHECK(ctx);
-        k_rs_scan<<<1, 1024, 0, ctx->stream>>>(g_hist, nb, g_base);
+        k_rs_scan_rows<<<256, 256, 0, ctx->stream>>>(g_hist, nb, g_base);
         KP_LAUNCH_CHECK(ctx);
         k_rs_scatter<K><<<nb, RS_THREADS, 0, ctx->stream>>>(kin, (p == 0 && vals_are_iota) ? nullptr : vin, kout, vout, n,
                                                             shift, g_hist, g_base, nb);

@@ -308,7 +308,7 @@ class PointCloud:
         stats = (C.c_double * 3)()
         hint = 0.0
         if hasattr(self, "_voxel_hint"):   # cloud came out of voxel_down_sample: its spacing sizes the search grid
-            hint = self._voxel_hint * 1.1 * float(np.sqrt(nb_neighbors / np.pi))
+            hint = self._voxel_hint * 1.5 * float(np.sqrt(nb_neighbors / np.pi))
         ctx.check(ctx.lib.kp_sor_mask(ctx.handle, pts.ptr, n, int(nb_neighbors), float(std_ratio), hint, keep.ptr, None,
                                       stats, C.byref(kept)))
         out, idx = self._select_mask(keep)

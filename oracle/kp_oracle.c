@@ -93,9 +93,6 @@ KPO_API double kpo_csum(const double *x, long n)
     free(owned);
     return r;
 }
-/* csum32: one group only (used for the per-query mean of <= k distances and
- * never more than a few hundred values): same lane/butterfly shape. */
-static double kpo_csum32(const double *x, long n) { return kpo_group1024(x, n); }
 
 /* --------------------------------------------------- K1 unproject (a1-a5) -- */
 /* Depth -> XYZ through the xy-table, then the per-sensor extrinsic.
@@ -452,8 +449,10 @@ KPO_API long kpo_sor(const float *pts, long n, int k, double std_ratio, double c
             int c = 0;
             if (!isnan(pts[3 * i])) kpo_query(&g, pts + 3 * i, k, 0.0, bd, bi, &c);
             if (c == 0) { mean[i] = -1.0; continue; }
-            for (int j = 0; j < c; ++j) bd[j] = sqrt(bd[j]);
-            mean[i] = kpo_csum32(bd, c) / (double)c;
+            /* std::accumulate over the neighbour distances in ascending (d2, index) order */
+            double acc = 0.0;
+            for (int j = 0; j < c; ++j) acc = acc + sqrt(bd[j]);
+            mean[i] = acc / (double)c;
         }
         free(bd); free(bi);
     }
