@@ -131,6 +131,7 @@ struct KpGrid {
     int2 *d_hvals = nullptr;         // (start, end) into d_sorted
     uint32_t hmask = 0;
     int32_t n_cells = 0;
+    uint32_t *d_bitmap = nullptr;    // cell occupancy bits (NULL when dim0*dim1*dim2 is too large)
 };
 // builds a grid over d_xyz in workspace memory (valid until kp_ws_reset). cell > 0 required.
 // h_bounds6: min/max xyz enclosing every non-NaN point (may be conservative); NULL -> computed here (one sync).

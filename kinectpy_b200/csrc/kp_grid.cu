@@ -276,6 +276,80 @@ __device__ __forceinline__ void kq_truncate(KqState &s)
     __syncwarp();
 }
 
+// ---- buffer maintenance without sorting: the buffer always holds EVERY candidate seen so far that is
+// below the bound tau.  When it fills, tau is lowered to a sampled pivot that still has >= k entries at or
+// below it (one counting pass + one in-place compaction); the exact order is only established once, by the
+// final kq_truncate.  (A bitonic sort per overflow, the first version, cost more than the search itself.)
+__device__ __forceinline__ int kq_warp_sum(int c)
+{
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) c += __shfl_xor_sync(KP_FULL, c, sft);
+    return c;
+}
+__device__ __forceinline__ int kq_count_le(const KqState &s, double pd, int pi)
+{
+    int c = 0;
+    for (int t = s.lane; t < s.n_buf; t += 32) c += !kq_less(pd, pi, s.bd[t], s.bi[t]);
+    return kq_warp_sum(c);
+}
+__device__ __forceinline__ int kq_count_d_le(const KqState &s, double lim)
+{
+    int c = 0;
+    for (int t = s.lane; t < s.n_buf; t += 32) c += s.bd[t] <= lim;
+    return kq_warp_sum(c);
+}
+__device__ __forceinline__ void kq_keep_le(KqState &s, double pd, int pi)
+{
+    int out = 0;
+    const unsigned lt = (1u << s.lane) - 1u;
+    for (int base = 0; base < s.n_buf; base += 32) {
+        const int t = base + s.lane;
+        const bool v = t < s.n_buf;
+        const double d = v ? s.bd[t] : 0.0;
+        const int i = v ? s.bi[t] : 0;
+        const bool keep = v && !kq_less(pd, pi, d, i);
+        const unsigned m = __ballot_sync(KP_FULL, keep);
+        __syncwarp();   // the whole chunk is in registers before anything (at an index <= t) is overwritten
+        if (keep) { int pos = out + __popc(m & lt); s.bd[pos] = d; s.bi[pos] = i; }
+        out += __popc(m);
+        __syncwarp();
+    }
+    s.n_buf = out;
+}
+__device__ void kq_tighten(KqState &s)
+{
+    // 32 evenly spaced samples, sorted across the lanes (bitonic network on shuffles)
+    const int si = (int)(((long long)s.lane * s.n_buf) >> 5);
+    double sd = s.bd[si];
+    int sid = s.bi[si];
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const double od = __shfl_xor_sync(KP_FULL, sd, stride);
+            const int oi = __shfl_xor_sync(KP_FULL, sid, stride);
+            const bool keep_min = ((s.lane & stride) == 0) == ((s.lane & size) == 0);
+            const bool other_less = kq_less(od, oi, sd, sid);
+            if (keep_min ? other_less : kq_less(sd, sid, od, oi)) { sd = od; sid = oi; }
+        }
+    }
+    // lowest sample quantile expected to keep ~1.5 k entries; verify by counting, move up if it keeps too few
+    int j = (int)((48LL * s.k) / s.n_buf);
+    if (j > 31) j = 31;
+    for (int tries = 0; tries < 6; ++tries) {
+        const double pd = __shfl_sync(KP_FULL, sd, j);
+        const int pi = __shfl_sync(KP_FULL, sid, j);
+        const int c = kq_count_le(s, pd, pi);
+        if (c >= s.k) {
+            if (c < s.n_buf) { kq_keep_le(s, pd, pi); s.tau_d = pd; s.tau_i = pi; }
+            break;
+        }
+        if (j == 31) break;
+        j = min(31, 2 * j + 1);
+    }
+    if (s.n_buf > s.cap - 32) kq_truncate(s);   // unlucky samples: fall back to the exact sort
+}
+
 __device__ __forceinline__ void kq_candidate(KqState &s, bool valid, float4 p, int mode)
 {
     double d = kp_d2(s.qx, s.qy, s.qz, (double)p.x, (double)p.y, (double)p.z);
@@ -293,7 +367,7 @@ __device__ __forceinline__ void kq_candidate(KqState &s, bool valid, float4 p, i
     }
     s.n_buf += __popc(m);
     __syncwarp();
-    if (s.n_buf > s.cap - 32) kq_truncate(s);
+    if (s.n_buf > s.cap - 32) kq_tighten(s);
 }
 
 __device__ __forceinline__ void kq_scan_ranges(const KpGridDev &g, int rs, int re, KqState &s, int mode)
@@ -489,10 +563,10 @@ __global__ void __launch_bounds__(KQ_WARPS * 32) k_knn(const __grid_constant__ K
             int ring = 1;
             if (p.mode != KQ_MODE_RADIUS) {
                 for (;;) {
-                    kq_truncate(s);
                     double safe = (double)ring * g.cell * (1.0 - 1.0 / 1048576.0);
                     double s2 = safe * safe;
-                    if (s.n_buf == s.k && s.tau_d <= s2) break;
+                    // certified as soon as k of the candidates seen so far lie inside the scanned radius
+                    if (s.n_buf >= s.k && kq_count_d_le(s, s2) >= s.k) break;
                     if (p.r2cap > 0 && p.r2cap <= s2) break;
                     if (ring >= maxring) break;
                     ++ring;
@@ -505,7 +579,6 @@ __global__ void __launch_bounds__(KQ_WARPS * 32) k_knn(const __grid_constant__ K
                             s.tau_d = p.r2cap > 0 ? p.r2cap : INFINITY;
                             s.tau_i = p.r2cap > 0 ? (int)0x80000000 : 0x7fffffff;
                             kq_scan_ranges(g, 0, lane == 0 ? g.npts : 0, s, p.mode);
-                            kq_truncate(s);
                             break;
                         }
                     }
@@ -542,7 +615,7 @@ __global__ void __launch_bounds__(KQ_WARPS * 32) k_knn(const __grid_constant__ K
         if (p.mode == KQ_MODE_RADIUS) {
             if (lane == 0) p.rcount[row] = s.rcount;
         } else {
-            __syncwarp();
+            kq_truncate(s);   // the one exact sort: ascending (d2, index), cut to k
             if (lane == 0) kq_finalize(p, row, qnan ? 0 : s.n_buf, s.bd, s.bi, 1);
         }
         __syncwarp();
@@ -705,8 +778,8 @@ int next_pow2(int v)
 
 int knn_launch_warp(kp_ctx *ctx, KnnParams &p, int64_t grid_queries)
 {
-    p.cap = next_pow2(p.k + 32);
-    if (p.cap < 64) p.cap = 64;
+    p.cap = next_pow2(4 * p.k > 128 ? 4 * p.k : 128);
+    if ((size_t)KQ_WARPS * p.cap * 12 > 96 * 1024) p.cap = next_pow2(p.k + 64 > 128 ? p.k + 64 : 128);
     size_t smem = (size_t)KQ_WARPS * p.cap * (sizeof(double) + sizeof(int));
     if (smem > 200 * 1024) return kp_set_err(ctx, KP_E_ARG, "k = %d neighbours is too many for the per-warp buffer", p.k);
     if (smem > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

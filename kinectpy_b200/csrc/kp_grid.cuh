@@ -12,6 +12,9 @@ struct KpGridDev {
                               // z-row are adjacent in the sorted array)
     int dim[3];
     int npts;                 // rows of pts (NaN rows, if any, sit at the end)
+    const uint32_t *bitmap;   // one bit per cell, index (cx*dim1 + cy)*dim2 + cz; NULL when the grid is too large.
+                              // Surfaces are thin: most of a query's 27 cells are empty, and a bitmap word comes
+                              // from L1 while a hash probe goes to L2
     double org[3];
     double cell, inv_cell;
 };
@@ -30,6 +33,10 @@ __device__ __forceinline__ int2 kp_cell_range(const KpGridDev &g, int cx, int cy
 {
     if ((unsigned)cx >= (unsigned)g.dim[0] || (unsigned)cy >= (unsigned)g.dim[1] || (unsigned)cz >= (unsigned)g.dim[2])
         return make_int2(0, 0);
+    if (g.bitmap) {
+        const long long b = ((long long)cx * g.dim[1] + cy) * g.dim[2] + cz;
+        if (!((__ldg(g.bitmap + (b >> 5)) >> (b & 31)) & 1u)) return make_int2(0, 0);
+    }
     const uint64_t key = kp_cell_key(g, cx, cy, cz);
     uint32_t h = (uint32_t)kp_mix64(key) & g.hmask;
     for (;;) {

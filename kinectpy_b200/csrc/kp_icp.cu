@@ -33,6 +33,7 @@ struct IcpParams {
     KpGridDev g;
     const float *tgt_normals;   // indexed by original target index
     double *cur;                // [ns][3] moving source
+    int32_t *corr;              // [ns] position of the matched target point in g.pts, -1 = none
     int ns;
     double r2;
     int pass, max_iter;
@@ -77,37 +78,41 @@ __device__ bool icp_solve6(double M[6][7], double *x)
     return true;
 }
 
-__global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(const __grid_constant__ IcpParams p)
+// Pass, part 1 (latency-bound, light on registers so many warps stay resident): apply the pending update
+// to the moving source, find each point's nearest target point inside max_corr, store its position.
+__global__ void __launch_bounds__(ICP_THREADS) k_icp_corr(const __grid_constant__ IcpParams p)
 {
-    __shared__ double sh[ICP_THREADS / 32][ICP_NV];
-    __shared__ double tot[ICP_NV];
-    __shared__ unsigned int s_ticket;
-    IcpState *st = p.st;
+    const IcpState *st = p.st;
     if (st->done) return;
     const KpGridDev &g = p.g;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    double U[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) U[i] = st->U[i];
-
-    double acc[ICP_NV];
-#pragma unroll
-    for (int i = 0; i < ICP_NV; ++i) acc[i] = 0.0;
-
-    for (int i = blockIdx.x * ICP_THREADS + tid; i < p.ns; i += gridDim.x * ICP_THREADS) {
-        double sx = p.cur[3 * (int64_t)i], sy = p.cur[3 * (int64_t)i + 1], sz = p.cur[3 * (int64_t)i + 2];
-        if (p.pass > 0) {
-            double x2 = kp_affine(U[0], U[1], U[2], U[3], sx, sy, sz);
-            double y2 = kp_affine(U[4], U[5], U[6], U[7], sx, sy, sz);
-            double z2 = kp_affine(U[8], U[9], U[10], U[11], sx, sy, sz);
-            sx = x2; sy = y2; sz = z2;
-            p.cur[3 * (int64_t)i] = sx; p.cur[3 * (int64_t)i + 1] = sy; p.cur[3 * (int64_t)i + 2] = sz;
-        }
-        if (isnan(sx) || g.dim[0] <= 0) continue;
+    const int i = blockIdx.x * ICP_THREADS + threadIdx.x;
+    if (i >= p.ns) return;
+    double sx = p.cur[3 * (int64_t)i], sy = p.cur[3 * (int64_t)i + 1], sz = p.cur[3 * (int64_t)i + 2];
+    if (p.pass > 0) {
+        const double *U = st->U;
+        double x2 = kp_affine(U[0], U[1], U[2], U[3], sx, sy, sz);
+        double y2 = kp_affine(U[4], U[5], U[6], U[7], sx, sy, sz);
+        double z2 = kp_affine(U[8], U[9], U[10], U[11], sx, sy, sz);
+        sx = x2; sy = y2; sz = z2;
+        p.cur[3 * (int64_t)i] = sx; p.cur[3 * (int64_t)i + 1] = sy; p.cur[3 * (int64_t)i + 2] = sz;
+    }
+    int bpos = -1;
+    if (!isnan(sx) && g.dim[0] > 0) {
         const int cx = kp_cell_coord(g, sx, 0), cy = kp_cell_coord(g, sy, 1), cz = kp_cell_coord(g, sz, 2);
         double bd = INFINITY;
-        int bi = -1, bpos = -1;
+        int bi = -1;
+        // Warm start: after the first passes the update is tiny and most points keep their partner.  The
+        // previous partner is a valid candidate, so its distance is an upper bound that lets the row pruning
+        // below skip almost every other row -- the search stays exhaustive (every row that could hold a
+        // closer or equally close point is still scanned), only cheaper.
+        if (p.pass > 0) {
+            const int prev = p.corr[i];
+            if (prev >= 0) {
+                const float4 q = __ldg(g.pts + prev);
+                const double d2 = kp_d2(sx, sy, sz, (double)q.x, (double)q.y, (double)q.z);
+                if (d2 < p.r2) { bd = d2; bi = __float_as_int(q.w); bpos = prev; }
+            }
+        }
         // distance to the faces of the own cell (x, y), shrunk a hair so rounding in the cell assignment can
         // never hide a closer point: a row of cells farther than the best match so far is skipped
         double glo[2], ghi[2];
@@ -121,29 +126,50 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(const __grid_constant_
         const int order[9] = {4, 1, 3, 5, 7, 0, 2, 6, 8};   // own row first
         for (int oi = 0; oi < 9; ++oi) {
             const int dx = order[oi] / 3 - 1, dy = order[oi] % 3 - 1;
-            {
-                const double gx = dx < 0 ? glo[0] : (dx > 0 ? ghi[0] : 0.0), gy = dy < 0 ? glo[1] : (dy > 0 ? ghi[1] : 0.0);
-                const double m2 = gx * gx + gy * gy;
-                if (m2 >= p.r2 || m2 > bd) continue;
-            }
-            {
-                int a = 0x7fffffff, b = 0;
+            const double gx = dx < 0 ? glo[0] : (dx > 0 ? ghi[0] : 0.0), gy = dy < 0 ? glo[1] : (dy > 0 ? ghi[1] : 0.0);
+            const double m2 = gx * gx + gy * gy;
+            if (m2 >= p.r2 || m2 > bd) continue;
+            int a = 0x7fffffff, b = 0;
 #pragma unroll
-                for (int dz = -1; dz <= 1; ++dz) {
-                    int2 r = kp_cell_range(g, cx + dx, cy + dy, cz + dz);
-                    if (r.y > r.x) { a = min(a, r.x); b = max(b, r.y); }
-                }
-                for (int t = a; t < b; ++t) {
-                    float4 q = __ldg(g.pts + t);
-                    double d2 = kp_d2(sx, sy, sz, (double)q.x, (double)q.y, (double)q.z);
-                    int id = __float_as_int(q.w);
-                    if (d2 < p.r2 && (d2 < bd || (d2 == bd && id < bi))) { bd = d2; bi = id; bpos = t; }
-                }
+            for (int dz = -1; dz <= 1; ++dz) {
+                int2 r = kp_cell_range(g, cx + dx, cy + dy, cz + dz);
+                if (r.y > r.x) { a = min(a, r.x); b = max(b, r.y); }
+            }
+            for (int t = a; t < b; ++t) {
+                float4 q = __ldg(g.pts + t);
+                double d2 = kp_d2(sx, sy, sz, (double)q.x, (double)q.y, (double)q.z);
+                int id = __float_as_int(q.w);
+                if (d2 < p.r2 && (d2 < bd || (d2 == bd && id < bi))) { bd = d2; bi = id; bpos = t; }
             }
         }
-        if (bi < 0) continue;
-        float4 q = __ldg(g.pts + bpos);
+    }
+    p.corr[i] = bpos;
+}
+
+// Pass, part 2 (streaming): accumulate the 29 normal-equation scalars over the matched pairs, reduce, and let
+// the last CTA solve and publish the next update.
+__global__ void __launch_bounds__(ICP_THREADS, 2) k_icp_pass(const __grid_constant__ IcpParams p)
+{
+    __shared__ double sh[ICP_THREADS / 32][ICP_NV];
+    __shared__ double tot[ICP_NV];
+    __shared__ unsigned int s_ticket;
+    IcpState *st = p.st;
+    if (st->done) return;
+    const KpGridDev &g = p.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    double acc[ICP_NV];
+#pragma unroll
+    for (int i = 0; i < ICP_NV; ++i) acc[i] = 0.0;
+
+    for (int i = blockIdx.x * ICP_THREADS + tid; i < p.ns; i += gridDim.x * ICP_THREADS) {
+        const int bpos = p.corr[i];
+        if (bpos < 0) continue;
+        const double sx = p.cur[3 * (int64_t)i], sy = p.cur[3 * (int64_t)i + 1], sz = p.cur[3 * (int64_t)i + 2];
+        const float4 q = __ldg(g.pts + bpos);
+        const int bi = __float_as_int(q.w);
         const double ex = sx - (double)q.x, ey = sy - (double)q.y, ez = sz - (double)q.z;
+        const double bd = (ex * ex + ey * ey) + ez * ez;
         const double nx = (double)p.tgt_normals[3 * (int64_t)bi], ny = (double)p.tgt_normals[3 * (int64_t)bi + 1],
                      nz = (double)p.tgt_normals[3 * (int64_t)bi + 2];
         const double r = (ex * nx + ey * ny) + ez * nz;
@@ -243,6 +269,7 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
     int grid = (int)kp_blocks(n_src > 0 ? n_src : 1, ICP_THREADS);
     if (grid > ctx->sm_count * 2) grid = ctx->sm_count * 2;
     KP_TRY(kp_ws(ctx, (size_t)(n_src > 0 ? n_src : 1) * 3, &p.cur));
+    KP_TRY(kp_ws(ctx, (size_t)(n_src > 0 ? n_src : 1), &p.corr));
     KP_TRY(kp_ws(ctx, (size_t)grid * ICP_NV, &p.slots));
     KP_TRY(kp_ws(ctx, 1, &p.st));
     IcpState init;
@@ -253,6 +280,8 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
     KP_LAUNCH_CHECK(ctx);
     for (int pass = 0; pass <= max_iter; ++pass) {
         p.pass = pass;
+        k_icp_corr<<<kp_blocks(n_src > 0 ? n_src : 1, ICP_THREADS), ICP_THREADS, 0, ctx->stream>>>(p);
+        KP_LAUNCH_CHECK(ctx);
         k_icp_pass<<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
         KP_LAUNCH_CHECK(ctx);
     }

@@ -200,7 +200,7 @@ int kp_prim_run_starts_u32(kp_ctx *ctx, int64_t n, const uint32_t *d_keys, int32
 namespace {
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
+constexpr int RS_ITEMS = 8;    // 2048-key tiles: enough CTAs to fill 148 SMs already at ~1 M keys
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
 
 template <class K>

@@ -37,8 +37,8 @@ if __name__ == "__main__":
     else:
         cfgs = []
         for k in (20, 50):
-            for base in (1.1, 1.5, 2.2):
-                for cm in (1, 4, 6, 10):
+            for base in (1.5,):
+                for cm in (1, 4, 8, 16):
                     cfgs.append(dict(SW_K=k, SW_BASE=base, KP_KNN_COARSE_MULT=cm))
         for c in cfgs:
             env = dict(os.environ, KP_DEBUG_KNN="1", **{a: str(b) for a, b in c.items()})
