@@ -127,8 +127,7 @@ struct KpGrid {
     int32_t dim[3] = {0, 0, 0};
     int sh_x = 0, sh_y = 0;      // packed cell key layout (cz low)
     float4 *d_sorted = nullptr;      // xyz + original index (int bits in .w), sorted by cell key
-    uint64_t *d_hkeys = nullptr;     // open addressing table: cell key (~0 = empty)
-    int2 *d_hvals = nullptr;         // (start, end) into d_sorted
+    uint4 *d_slots = nullptr;        // open addressing table of 16-byte slots {key lo, key hi, start, end}
     uint32_t hmask = 0;
     int32_t n_cells = 0;
     uint32_t *d_bitmap = nullptr;    // cell occupancy bits (NULL when dim0*dim1*dim2 is too large)

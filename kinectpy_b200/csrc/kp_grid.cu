@@ -19,11 +19,12 @@
 KpGridDev kp_grid_dev(const KpGrid &g)
 {
     KpGridDev d;
-    d.pts = g.d_sorted; d.hkeys = g.d_hkeys; d.hvals = g.d_hvals; d.hmask = g.hmask;
+    d.pts = g.d_sorted; d.slots = g.d_slots; d.hmask = g.hmask;
     d.sh_x = g.sh_x; d.sh_y = g.sh_y;
     for (int c = 0; c < 3; ++c) { d.dim[c] = g.dim[c]; d.org[c] = g.org[c]; }
     d.cell = g.cell; d.inv_cell = g.inv_cell;
     d.npts = g.n;
+    d.bitmap = g.d_bitmap;
     return d;
 }
 
@@ -50,7 +51,8 @@ __global__ void __launch_bounds__(256) k_grid_keys(const float *xyz, int64_t n, 
 template <class K>
 __global__ void __launch_bounds__(256) k_grid_insert(const K *keys_sorted, const int32_t *run_start, const int32_t *d_R,
                                                      int n, unsigned long long sentinel, int has_sentinel,
-                                                     uint64_t *hkeys, int2 *hvals, uint32_t hmask)
+                                                     uint4 *slots, uint32_t hmask, uint32_t *bitmap, int sh_x, int sh_y,
+                                                     int dim1, int dim2)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     int R = *d_R;
@@ -58,10 +60,17 @@ __global__ void __launch_bounds__(256) k_grid_insert(const K *keys_sorted, const
     int a = run_start[r], b = (r + 1 < R) ? run_start[r + 1] : n;
     unsigned long long key = (unsigned long long)keys_sorted[a];
     if (has_sentinel && key == sentinel) return;
+    if (bitmap) {
+        const long long cx = (long long)(key >> sh_x), cy = (long long)((key >> sh_y) & ((1ull << (sh_x - sh_y)) - 1ull)),
+                        cz = (long long)(key & ((1ull << sh_y) - 1ull));
+        const long long bit = (cx * dim1 + cy) * dim2 + cz;
+        atomicOr(bitmap + (bit >> 5), 1u << (bit & 31));
+    }
     uint32_t h = (uint32_t)kp_mix64(key) & hmask;
     for (;;) {
-        unsigned long long prev = atomicCAS((unsigned long long *)(hkeys + h), ~0ull, key);
-        if (prev == ~0ull) { hvals[h] = make_int2(a, b); return; }
+        // claim the key half of the slot, then fill the value half (readers only run in later kernels)
+        unsigned long long prev = atomicCAS((unsigned long long *)(slots + h), ~0ull, key);
+        if (prev == ~0ull) { reinterpret_cast<int2 *>(slots + h)[1] = make_int2(a, b); return; }
         h = (h + 1) & hmask;
     }
 }
@@ -111,10 +120,15 @@ int grid_sort_build(kp_ctx *ctx, const float *d_xyz, int64_t n, KpGrid *g, int t
     if (run_start_out) *run_start_out = run_start;
     if (d_R_out) *d_R_out = d_R;
     if (!build_hash) return KP_OK;
-    KP_PROFB(ctx, "grid_hash", ((double)g->hmask + 1.0) * 8.0 + (double)n * (4.0 + 12.0 + 16.0));
-    KP_CUDA(ctx, cudaMemsetAsync(g->d_hkeys, 0xff, sizeof(uint64_t) * ((size_t)g->hmask + 1), ctx->stream));
-    k_grid_insert<K><<<kp_blocks(n, 256), 256, 0, ctx->stream>>>(keys_sorted, run_start, d_R, (int)n, sentinel, 1, g->d_hkeys,
-                                                                 g->d_hvals, g->hmask);
+    KP_PROFB(ctx, "grid_hash", ((double)g->hmask + 1.0) * 16.0 + (double)n * (4.0 + 12.0 + 16.0));
+    KP_CUDA(ctx, cudaMemsetAsync(g->d_slots, 0xff, sizeof(uint4) * ((size_t)g->hmask + 1), ctx->stream));
+    if (g->d_bitmap) {
+        size_t words = (size_t)(((long long)g->dim[0] * g->dim[1] * g->dim[2] + 31) / 32);
+        KP_CUDA(ctx, cudaMemsetAsync(g->d_bitmap, 0, words * sizeof(uint32_t), ctx->stream));
+    }
+    k_grid_insert<K><<<kp_blocks(n, 256), 256, 0, ctx->stream>>>(keys_sorted, run_start, d_R, (int)n, sentinel, 1, g->d_slots,
+                                                                 g->hmask, g->d_bitmap, g->sh_x, g->sh_y, g->dim[1],
+                                                                 g->dim[2]);
     KP_LAUNCH_CHECK(ctx);
     k_grid_gather<<<kp_blocks(n, 256), 256, 0, ctx->stream>>>(d_xyz, vals_sorted, n, g->d_sorted);
     KP_LAUNCH_CHECK(ctx);
@@ -175,9 +189,10 @@ int kp_grid_build(kp_ctx *ctx, const float *d_xyz, int64_t n, double cell, const
     uint32_t cap = 1024;
     while ((double)cap < want) cap <<= 1;
     g->hmask = cap - 1;
-    KP_TRY(kp_ws(ctx, (size_t)cap, &g->d_hkeys));
-    KP_TRY(kp_ws(ctx, (size_t)cap, &g->d_hvals));
+    KP_TRY(kp_ws(ctx, (size_t)cap, &g->d_slots));
     KP_TRY(kp_ws(ctx, (size_t)n, &g->d_sorted));
+    if (ncell <= 134217728.0)   // <= 16 MiB of occupancy bits
+        KP_TRY(kp_ws(ctx, (size_t)(ncell / 32.0) + 2, &g->d_bitmap));
     if (total_bits + 1 <= 32) return grid_sort_build<uint32_t>(ctx, d_xyz, n, g, total_bits, sentinel, nullptr, nullptr, true);
     return grid_sort_build<uint64_t>(ctx, d_xyz, n, g, total_bits, sentinel, nullptr, nullptr, true);
 }
@@ -712,12 +727,8 @@ __global__ void __launch_bounds__(TQ_THREADS) k_knn_tq(const __grid_constant__ K
             if (n == k && m2 > topd) continue;
             if (capped && m2 >= p.r2cap) continue;
         }
-        int a = 0x7fffffff, b = 0;
-#pragma unroll
-        for (int dz = -1; dz <= 1; ++dz) {
-            int2 r = kp_cell_range(g, cx + dx, cy + dy, cz + dz);
-            if (r.y > r.x) { a = min(a, r.x); b = max(b, r.y); }
-        }
+        const int2 rr = kp_row_range(g, cx + dx, cy + dy, cz);
+        const int a = rr.x, b = rr.y;
         // four candidates per trip: the loads and the four distance chains are independent, only the
         // offers are sequential (keeps the FP64 pipe busy at the low occupancy a per-thread heap allows)
         for (int t = a; t < b; t += 4) {

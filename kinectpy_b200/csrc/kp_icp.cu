@@ -129,13 +129,8 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_corr(const __grid_constant_
             const double gx = dx < 0 ? glo[0] : (dx > 0 ? ghi[0] : 0.0), gy = dy < 0 ? glo[1] : (dy > 0 ? ghi[1] : 0.0);
             const double m2 = gx * gx + gy * gy;
             if (m2 >= p.r2 || m2 > bd) continue;
-            int a = 0x7fffffff, b = 0;
-#pragma unroll
-            for (int dz = -1; dz <= 1; ++dz) {
-                int2 r = kp_cell_range(g, cx + dx, cy + dy, cz + dz);
-                if (r.y > r.x) { a = min(a, r.x); b = max(b, r.y); }
-            }
-            for (int t = a; t < b; ++t) {
+            const int2 rr = kp_row_range(g, cx + dx, cy + dy, cz);
+            for (int t = rr.x; t < rr.y; ++t) {
                 float4 q = __ldg(g.pts + t);
                 double d2 = kp_d2(sx, sy, sz, (double)q.x, (double)q.y, (double)q.z);
                 int id = __float_as_int(q.w);
