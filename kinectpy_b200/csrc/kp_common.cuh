@@ -130,11 +130,16 @@ struct KpGrid {
     uint4 *d_slots = nullptr;        // open addressing table of 16-byte slots {key lo, key hi, start, end}
     uint32_t hmask = 0;
     int32_t n_cells = 0;
-    uint32_t *d_bitmap = nullptr;    // cell occupancy bits (NULL when dim0*dim1*dim2 is too large)
+    uint2 *d_cellmap = nullptr;      // {~occupancy bits, first rank} per 32 cells (NULL when dim0*dim1*dim2 is too large)
+    int32_t *d_run_start = nullptr;  // [occupied cells + 1]
+    int rad = 1;                     // block radius (in cells) the cell edge was chosen for: a search covers (2 rad + 1)^3 cells
 };
 // builds a grid over d_xyz in workspace memory (valid until kp_ws_reset). cell > 0 required.
 // h_bounds6: min/max xyz enclosing every non-NaN point (may be conservative); NULL -> computed here (one sync).
 int kp_grid_build(kp_ctx *ctx, const float *d_xyz, int64_t n, double cell, const float *h_bounds6, KpGrid *g);
+// grid for a neighbour search whose 27-cell block would have edge `cell`: builds it with rad = 2 and half
+// the edge when the histogram kernels will run the search (k <= 64), so that the block can be pruned column by column
+int kp_grid_build_knn(kp_ctx *ctx, const float *d_xyz, int64_t n, double cell, int k, const float *h_bounds6, KpGrid *g);
 // picks a cell edge so that an occupied cell holds ~target points (one trial sort)
 int kp_grid_auto_cell(kp_ctx *ctx, const float *d_xyz, int64_t n, const float *h_bounds6, double target_per_cell,
                       double *cell_out);

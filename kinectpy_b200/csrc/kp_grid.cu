@@ -24,7 +24,7 @@ KpGridDev kp_grid_dev(const KpGrid &g)
     for (int c = 0; c < 3; ++c) { d.dim[c] = g.dim[c]; d.org[c] = g.org[c]; }
     d.cell = g.cell; d.inv_cell = g.inv_cell;
     d.npts = g.n;
-    d.bitmap = g.d_bitmap;
+    d.cellmap = g.d_cellmap; d.run_start = g.d_run_start;
     return d;
 }
 
@@ -49,22 +49,26 @@ __global__ void __launch_bounds__(256) k_grid_keys(const float *xyz, int64_t n, 
 }
 
 template <class K>
-__global__ void __launch_bounds__(256) k_grid_insert(const K *keys_sorted, const int32_t *run_start, const int32_t *d_R,
+__global__ void __launch_bounds__(256) k_grid_insert(const K *keys_sorted, int32_t *run_start, const int32_t *d_R,
                                                      int n, unsigned long long sentinel, int has_sentinel,
-                                                     uint4 *slots, uint32_t hmask, uint32_t *bitmap, int sh_x, int sh_y,
+                                                     uint4 *slots, uint32_t hmask, uint2 *cellmap, int sh_x, int sh_y,
                                                      int dim1, int dim2)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     int R = *d_R;
     if (r >= R) return;
+    if (r == 0) run_start[R] = n;   // closes the last run (read by later kernels only)
     int a = run_start[r], b = (r + 1 < R) ? run_start[r + 1] : n;
     unsigned long long key = (unsigned long long)keys_sorted[a];
     if (has_sentinel && key == sentinel) return;
-    if (bitmap) {
+    if (cellmap) {
+        // runs are in key order = cell-index order, so r is the rank of this cell among the occupied ones
         const long long cx = (long long)(key >> sh_x), cy = (long long)((key >> sh_y) & ((1ull << (sh_x - sh_y)) - 1ull)),
                         cz = (long long)(key & ((1ull << sh_y) - 1ull));
         const long long bit = (cx * dim1 + cy) * dim2 + cz;
-        atomicOr(bitmap + (bit >> 5), 1u << (bit & 31));
+        atomicAnd(&cellmap[bit >> 5].x, ~(1u << (bit & 31)));
+        atomicMin(&cellmap[bit >> 5].y, (unsigned)r);
+        return;
     }
     uint32_t h = (uint32_t)kp_mix64(key) & hmask;
     for (;;) {
@@ -120,14 +124,13 @@ int grid_sort_build(kp_ctx *ctx, const float *d_xyz, int64_t n, KpGrid *g, int t
     if (run_start_out) *run_start_out = run_start;
     if (d_R_out) *d_R_out = d_R;
     if (!build_hash) return KP_OK;
-    KP_PROFB(ctx, "grid_hash", ((double)g->hmask + 1.0) * 16.0 + (double)n * (4.0 + 12.0 + 16.0));
-    KP_CUDA(ctx, cudaMemsetAsync(g->d_slots, 0xff, sizeof(uint4) * ((size_t)g->hmask + 1), ctx->stream));
-    if (g->d_bitmap) {
-        size_t words = (size_t)(((long long)g->dim[0] * g->dim[1] * g->dim[2] + 31) / 32);
-        KP_CUDA(ctx, cudaMemsetAsync(g->d_bitmap, 0, words * sizeof(uint32_t), ctx->stream));
-    }
+    g->d_run_start = run_start;
+    const size_t words = (size_t)(((long long)g->dim[0] * g->dim[1] * g->dim[2] + 31) / 32) + 1;
+    const size_t table_bytes = g->d_cellmap ? words * sizeof(uint2) : ((size_t)g->hmask + 1) * sizeof(uint4);
+    KP_PROFB(ctx, "grid_hash", (double)table_bytes + (double)n * (4.0 + 12.0 + 16.0));
+    KP_CUDA(ctx, cudaMemsetAsync(g->d_cellmap ? (void *)g->d_cellmap : (void *)g->d_slots, 0xff, table_bytes, ctx->stream));
     k_grid_insert<K><<<kp_blocks(n, 256), 256, 0, ctx->stream>>>(keys_sorted, run_start, d_R, (int)n, sentinel, 1, g->d_slots,
-                                                                 g->hmask, g->d_bitmap, g->sh_x, g->sh_y, g->dim[1],
+                                                                 g->hmask, g->d_cellmap, g->sh_x, g->sh_y, g->dim[1],
                                                                  g->dim[2]);
     KP_LAUNCH_CHECK(ctx);
     k_grid_gather<<<kp_blocks(n, 256), 256, 0, ctx->stream>>>(d_xyz, vals_sorted, n, g->d_sorted);
@@ -188,13 +191,25 @@ int kp_grid_build(kp_ctx *ctx, const float *d_xyz, int64_t n, double cell, const
     double want = 2.0 * ((double)n < ncell ? (double)n : ncell);
     uint32_t cap = 1024;
     while ((double)cap < want) cap <<= 1;
-    g->hmask = cap - 1;
-    KP_TRY(kp_ws(ctx, (size_t)cap, &g->d_slots));
     KP_TRY(kp_ws(ctx, (size_t)n, &g->d_sorted));
-    if (ncell <= 134217728.0)   // <= 16 MiB of occupancy bits
-        KP_TRY(kp_ws(ctx, (size_t)(ncell / 32.0) + 2, &g->d_bitmap));
+    const bool force_hash = getenv("KP_GRID_FORCE_HASH") != nullptr;   // test hook: exercise the huge-grid path
+    if (ncell <= 134217728.0 && !force_hash) {   // <= 32 MiB of cell map
+        KP_TRY(kp_ws(ctx, (size_t)(ncell / 32.0) + 2, &g->d_cellmap));
+    } else {
+        g->hmask = cap - 1;
+        KP_TRY(kp_ws(ctx, (size_t)cap, &g->d_slots));
+    }
     if (total_bits + 1 <= 32) return grid_sort_build<uint32_t>(ctx, d_xyz, n, g, total_bits, sentinel, nullptr, nullptr, true);
     return grid_sort_build<uint64_t>(ctx, d_xyz, n, g, total_bits, sentinel, nullptr, nullptr, true);
+}
+
+int kp_grid_build_knn(kp_ctx *ctx, const float *d_xyz, int64_t n, double cell, int k, const float *h_bounds6, KpGrid *g)
+{
+    static const int want = getenv("KP_KNN_RAD") ? atoi(getenv("KP_KNN_RAD")) : 2;
+    const int rad = (k <= 64 && want == 2) ? 2 : 1;
+    KP_TRY(kp_grid_build(ctx, d_xyz, n, cell / (double)rad, h_bounds6, g));
+    g->rad = rad;
+    return KP_OK;
 }
 
 int kp_grid_auto_cell(kp_ctx *ctx, const float *d_xyz, int64_t n, const float *h_bounds6, double target_per_cell,
@@ -242,6 +257,7 @@ struct KnnParams {
     const float *queries;   // NULL -> the cloud queries itself, in cell-sorted order
     int64_t nq;
     int k, cap, mode;
+    int rad;                // level-0 block radius in cells (1: 27 cells, 2: 125 cells) the grid was sized for
     double r2cap;           // > 0: only neighbours with d2 < r2cap
     int32_t *idx; double *d2; int32_t *count; double *mean;
     const float *cloud; float *normals;
@@ -392,10 +408,19 @@ __device__ __forceinline__ void kq_scan_ranges(const KpGridDev &g, int rs, int r
         int j = __ffs(m) - 1;
         m &= m - 1;
         int a = __shfl_sync(KP_FULL, rs, j), b = __shfl_sync(KP_FULL, re, j);
-        for (int t = a; t < b; t += 32) {
-            bool v = t + s.lane < b;
-            float4 p = v ? __ldg(g.pts + t + s.lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-            kq_candidate(s, v, p, mode);
+        // four coalesced loads in flight per lane before the (sequential) candidate handling
+        for (int t = a; t < b; t += 128) {
+            const int i0 = t + s.lane;
+            const bool v0 = i0 < b, v1 = i0 + 32 < b, v2 = i0 + 64 < b, v3 = i0 + 96 < b;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 p0 = v0 ? __ldg(g.pts + i0) : z4;
+            const float4 p1 = v1 ? __ldg(g.pts + i0 + 32) : z4;
+            const float4 p2 = v2 ? __ldg(g.pts + i0 + 64) : z4;
+            const float4 p3 = v3 ? __ldg(g.pts + i0 + 96) : z4;
+            kq_candidate(s, v0, p0, mode);
+            if (t + 32 < b) kq_candidate(s, v1, p1, mode);
+            if (t + 64 < b) kq_candidate(s, v2, p2, mode);
+            if (t + 96 < b) kq_candidate(s, v3, p3, mode);
         }
     }
 }
@@ -637,147 +662,423 @@ __global__ void __launch_bounds__(KQ_WARPS * 32) k_knn(const __grid_constant__ K
     }
 }
 
-// ---- thread-per-query kernel (the fast path, k <= TQ_KMAX, the cloud queries itself).
-// Queries are taken in cell-sorted order, so the lanes of a warp sit in the same or adjacent cells and
-// walk (almost) the same candidate ranges: their 16-byte candidate loads hit the same L1 lines, which is
-// the shared staging of the cell neighbourhood.  Each thread keeps a max-heap of its k best (d2, index)
-// pairs in shared memory, laid out [slot][thread] so that any slot pattern is bank-conflict free.
-// Rows of cells whose nearest face is already farther than the current k-th distance are skipped.
-// A query whose k-th distance is not certified by the 27-cell block (isolated points: what SOR is
-// looking for) is appended to a straggler list and finished by the warp kernel above.
-constexpr int TQ_THREADS = 128;
-constexpr int TQ_KMAX = 64;
+// ---- histogram-select kernels (the fast path: k <= HQ_KMAX, the cloud queries itself).
+// Selection never maintains a running top-k.  Pass 1 histograms the fp32 squared distances of the 27-cell
+// block over [0, R^2) (R = the radius the block certifies); the first bin b whose cumulative count
+// reaches k bounds the k-th distance.  Pass 2 re-walks the block (L1-resident) and collects the
+// candidates of bins <= b -- k plus a handful -- counting-sorted by bin through the histogram's prefix
+// sums.  Only those are evaluated in double: sorted, checked to be strictly ascending in the canonical
+// (d2, index) order, and certified against the lower edge of the uncollected bins.  fp32 is used for
+// binning only: a bin index is a monotone function of the fp32 distance, whose relative error (< 6e-7)
+// is covered by the 1e-6 margins of the certificate, so the result is the exact double-precision answer
+// or the query is handed to the next level (flag), never an approximation.
+constexpr int HQ_THREADS = 128;
+constexpr int HQ_KMAX = 64;
+constexpr float HQ_MAGIC = 8388608.0f;          // 2^23: adding it leaves round(x) in the low mantissa bits
+constexpr int HQ_MAGIC_BITS = 0x4B000000;
 
-__device__ __forceinline__ bool tq_greater(double d, int i, double e, int j) { return d > e || (d == e && i > j); }
+__device__ __forceinline__ float hq_d32(float qx, float qy, float qz, const float4 &c)
+{
+    const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+}
+__device__ __forceinline__ int hq_bin(float d, float scale)
+{
+    return __float_as_int(__fmaf_rn(d, scale, HQ_MAGIC)) - HQ_MAGIC_BITS;   // round(d * scale), monotone in d
+}
+__device__ __forceinline__ bool hq_before(double d, int i, double e, int j) { return d < e || (d == e && i < j); }
 
-__global__ void __launch_bounds__(TQ_THREADS) k_knn_tq(const __grid_constant__ KnnParams p)
+// geometry of one query against the grid: own cell, gaps to its faces, certified radius, bin scale
+struct HqGeom {
+    int cx, cy, cz;
+    float flo[3], fhi[3], fcs;   // fp32 lower bounds (shrunk by 1e-6) of the gaps to the own cell's faces and of
+                                 // the cell edge: cells are pruned in fp32, always on the safe side
+    double R2;          // binning range: min(certified radius^2, cap)
+    double Rcert2;      // every point closer than sqrt(Rcert2) lies inside the (2R+1)^3-cell block
+    bool cap_binding;   // the radius cap, not the block, ends the range: nothing eligible lies outside it
+    float scale;
+};
+__device__ __forceinline__ void hq_geom(const KpGridDev &g, double qx, double qy, double qz, double r2cap, int nb,
+                                        bool clamp, int R, HqGeom &o)
+{
+    const double shrink = 1.0 - 1.0 / 1048576.0;
+    o.cx = kp_cell_coord(g, qx, 0); o.cy = kp_cell_coord(g, qy, 1); o.cz = kp_cell_coord(g, qz, 2);
+    if (clamp) {
+        o.cx = min(max(o.cx, 0), g.dim[0] - 1); o.cy = min(max(o.cy, 0), g.dim[1] - 1); o.cz = min(max(o.cz, 0), g.dim[2] - 1);
+    }
+    const double qq[3] = {qx, qy, qz};
+    const int cc[3] = {o.cx, o.cy, o.cz};
+    double mg = INFINITY;
+    const double cs = g.cell * shrink;
+    o.fcs = (float)(cs * (1.0 - 1e-6));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double f = (qq[c] - g.org[c]) * g.inv_cell - (double)cc[c];
+        f = fmin(fmax(f, 0.0), 1.0);
+        const double lo = f * cs, hi = (1.0 - f) * cs;
+        o.flo[c] = (float)(lo * (1.0 - 1e-6)); o.fhi[c] = (float)(hi * (1.0 - 1e-6));
+        mg = fmin(mg, fmin(lo, hi));
+    }
+    const double safe = (double)R * cs + mg;
+    o.Rcert2 = safe * safe;
+    o.R2 = o.Rcert2;
+    o.cap_binding = false;
+    if (r2cap > 0) {
+        const double capw = r2cap * (1.0 + 2e-6);      // every candidate with d2 < r2cap has fp32 d2 < capw
+        if (capw <= o.Rcert2) { o.R2 = capw; o.cap_binding = true; }
+    }
+    o.scale = (float)((double)(nb - 1) / o.R2);        // bins 0..nb-1 cover fp32 d2 < R2 * (nb - 0.5) / (nb - 1)
+}
+// fp32 lower bound of the distance from the query to the cells at offset d (in cells) along axis c
+__device__ __forceinline__ float hq_gap(const HqGeom &G, int c, int d)
+{
+    const float g0 = d < 0 ? G.flo[c] : G.fhi[c];
+    return d == 0 ? 0.0f : g0 + (float)(abs(d) - 1) * G.fcs;
+}
+// fp32 upper bound of a squared-distance budget, with room for the rounding of the fp32 gap arithmetic
+__device__ __forceinline__ float hq_budget(double b) { return __double2float_ru(b * (1.0 + 4e-6)); }
+// [start,end) of the part of the z-column (cx+dx, cy+dy) that can hold a point with d2 <= budget; (0,0) if none.
+// Monotone in budget: a cell visited under a budget is visited under every larger one.
+__device__ __forceinline__ int2 hq_column(const KpGridDev &g, const HqGeom &G, int dx, int dy, int R, float budget)
+{
+    const float gx = hq_gap(G, 0, dx), gy = hq_gap(G, 1, dy);
+    const float zb = budget - (gx * gx + gy * gy);
+    if (!(zb >= 0.0f)) return make_int2(0, 0);
+    int zlo = G.cz, zhi = G.cz;
+    for (int j = 1; j <= R; ++j) { const float gz = hq_gap(G, 2, -j); if (gz * gz <= zb) zlo = G.cz - j; else break; }
+    for (int j = 1; j <= R; ++j) { const float gz = hq_gap(G, 2, j); if (gz * gz <= zb) zhi = G.cz + j; else break; }
+    return kp_span_range(g, G.cx + dx, G.cy + dy, zlo, zhi);
+}
+// columns of the block: the 9 inner ones first, then the ring at Chebyshev distance 2
+__constant__ signed char HQ_COLS[25][2] = {
+    {0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1},
+    {-2, 0}, {2, 0}, {0, -2}, {0, 2}, {-2, -1}, {-2, 1}, {2, -1}, {2, 1}, {-1, -2}, {1, -2}, {-1, 2}, {1, 2},
+    {-2, -2}, {2, -2}, {-2, 2}, {2, 2}};
+// smallest double-precision d2 a candidate outside bins 0..b can have
+__device__ __forceinline__ double hq_lower_edge(int b, float scale) { return ((double)b + 0.5) / (double)scale * (1.0 - 1e-6); }
+
+__device__ void kq_finish_normal(const KnnParams &p, int64_t row, int cnt, double *sm)
+{
+    double nr[3] = {0.0, 0.0, 1.0};
+    if (cnt >= 3) {
+        double inv = (double)cnt;
+        for (int c = 0; c < 9; ++c) sm[c] /= inv;
+        double cov[6] = {sm[3] - sm[0] * sm[0], sm[4] - sm[0] * sm[1], sm[5] - sm[0] * sm[2],
+                         sm[6] - sm[1] * sm[1], sm[7] - sm[1] * sm[2], sm[8] - sm[2] * sm[2]};
+        kq_smallest_eigvec(cov, nr);
+        if (nr[0] == 0.0 && nr[1] == 0.0 && nr[2] == 0.0) nr[2] = 1.0;
+    }
+    p.normals[3 * row] = (float)nr[0]; p.normals[3 * row + 1] = (float)nr[1]; p.normals[3 * row + 2] = (float)nr[2];
+}
+
+template <int NB>
+__global__ void __launch_bounds__(HQ_THREADS) k_knn_hist(const __grid_constant__ KnnParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const KpGridDev &g = p.g;
     const int tid = threadIdx.x;
-    const int64_t w = (int64_t)blockIdx.x * TQ_THREADS + tid;
+    const int64_t w = (int64_t)blockIdx.x * HQ_THREADS + tid;
     if (w >= p.nq) return;
-    const int64_t q = p.qlist ? (int64_t)p.qlist[w] : w;
-    double *hd = reinterpret_cast<double *>(smem_raw) + tid;                                   // hd[slot * TQ_THREADS]
-    int *hi = reinterpret_cast<int *>(reinterpret_cast<double *>(smem_raw) + (size_t)p.k * TQ_THREADS) + tid;
-    const int k = p.k;
+    const int64_t q = w;
+    // buf[slot * HQ_THREADS], hist[bin * HQ_THREADS]: any slot pattern is bank-conflict free
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem_raw) + tid;
+    unsigned short *hist = reinterpret_cast<unsigned short *>(smem_raw + (size_t)p.cap * HQ_THREADS * sizeof(unsigned long long)) + tid;
+    const int k = p.k, R = p.rad;
     const float4 me = __ldg(p.qpts + q);
     const int64_t row = __float_as_int(me.w);
     const double qx = (double)me.x, qy = (double)me.y, qz = (double)me.z;
-    if (isnan(qx)) { kq_finalize(p, row, 0, hd, hi, TQ_THREADS); return; }
-    const int cx = kp_cell_coord(g, qx, 0), cy = kp_cell_coord(g, qy, 1), cz = kp_cell_coord(g, qz, 2);
-    // distance from the query to the faces of its own cell, per axis (low, high), slightly shrunk so
-    // that rounding in the cell assignment can never make a pruned row hold a closer point
-    const double shrink = 1.0 - 1.0 / 1048576.0;
-    double glo[3], ghi[3];
-    {
-        const double qq[3] = {qx, qy, qz};
-        const int cc[3] = {cx, cy, cz};
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            double f = (qq[c] - g.org[c]) * g.inv_cell - (double)cc[c];
-            f = fmin(fmax(f, 0.0), 1.0);
-            glo[c] = f * g.cell * shrink;
-            ghi[c] = (1.0 - f) * g.cell * shrink;
-        }
+    if (isnan(me.x)) {
+        if (p.mode == KQ_MODE_KNN) kq_finalize(p, row, 0, nullptr, nullptr, 0);
+        else { double sm[9]; kq_finish_normal(p, row, 0, sm); }
+        return;
     }
-    int n = 0;
-    const bool capped = p.r2cap > 0;
-    // the heap's root (current k-th best) is mirrored in registers: the common "reject" test touches no memory
-    double topd = INFINITY;
-    int topi = 0x7fffffff;
-    auto offer = [&](double d, int id) {
-        if (capped && !(d < p.r2cap)) return;
-        if (n < k) {
-            int pos = n++;   // push: sift up
-            while (pos > 0) {
-                int par = (pos - 1) >> 1;
-                double pd = hd[par * TQ_THREADS]; int pi = hi[par * TQ_THREADS];
-                if (!tq_greater(d, id, pd, pi)) break;
-                hd[pos * TQ_THREADS] = pd; hi[pos * TQ_THREADS] = pi;
-                pos = par;
+    HqGeom G;
+    hq_geom(g, qx, qy, qz, p.r2cap, NB, false, R, G);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) hist[j * HQ_THREADS] = 0;
+    // ---- pass 1: histogram of the fp32 distances.  Phase A = the 9 inner columns; its histogram bounds the
+    // k-th distance, and phase B (the outer ring, R = 2) only visits the cells that reach inside that bound.
+    // Invariant: every candidate with d2 < budget has been visited.
+    const int ncols = (2 * R + 1) * (2 * R + 1);
+    double budget = G.R2;
+    float fbudget = hq_budget(budget);
+    bool bounded = false;                       // phase A alone reached k
+    for (int ci = 0; ci < ncols; ++ci) {
+        if (ci == 9) {
+            int cum = 0;
+            for (int j = 0; j < NB; ++j) {
+                cum += hist[j * HQ_THREADS];
+                if (cum >= k) { budget = fmin(budget, ((double)j + 1.0) / (double)G.scale); bounded = true; break; }
             }
-            hd[pos * TQ_THREADS] = d; hi[pos * TQ_THREADS] = id;
-            if (n == k) { topd = hd[0]; topi = hi[0]; }
-        } else if (tq_greater(topd, topi, d, id)) {
-            int pos = 0;     // replace the current worst: sift down
-            for (;;) {
-                int ch = 2 * pos + 1;
-                if (ch >= k) break;
-                double cd = hd[ch * TQ_THREADS]; int ci = hi[ch * TQ_THREADS];
-                if (ch + 1 < k) {
-                    double ed = hd[(ch + 1) * TQ_THREADS]; int ei = hi[(ch + 1) * TQ_THREADS];
-                    if (tq_greater(ed, ei, cd, ci)) { cd = ed; ci = ei; ++ch; }
-                }
-                if (!tq_greater(cd, ci, d, id)) break;
-                hd[pos * TQ_THREADS] = cd; hi[pos * TQ_THREADS] = ci;
-                pos = ch;
-            }
-            hd[pos * TQ_THREADS] = d; hi[pos * TQ_THREADS] = id;
-            topd = hd[0]; topi = hi[0];
+            fbudget = hq_budget(budget);
         }
-    };
-    // rows ordered so the query's own row comes first (tightens the k-th distance early)
-    const int order[9] = {4, 1, 3, 5, 7, 0, 2, 6, 8};
-    for (int oi = 0; oi < 9; ++oi) {
-        const int dx = order[oi] / 3 - 1, dy = order[oi] % 3 - 1;
-        if (n == k || capped) {
-            const double gx = dx < 0 ? glo[0] : (dx > 0 ? ghi[0] : 0.0), gy = dy < 0 ? glo[1] : (dy > 0 ? ghi[1] : 0.0);
-            const double m2 = gx * gx + gy * gy;
-            if (n == k && m2 > topd) continue;
-            if (capped && m2 >= p.r2cap) continue;
-        }
-        const int2 rr = kp_row_range(g, cx + dx, cy + dy, cz);
-        const int a = rr.x, b = rr.y;
-        // four candidates per trip: the loads and the four distance chains are independent, only the
-        // offers are sequential (keeps the FP64 pipe busy at the low occupancy a per-thread heap allows)
-        for (int t = a; t < b; t += 4) {
-            const int m = b - t;
+        const int2 rr = hq_column(g, G, HQ_COLS[ci][0], HQ_COLS[ci][1], R, fbudget);
+        for (int t = rr.x; t < rr.y; t += 4) {
+            const int m = rr.y - t;
             const float4 c0 = __ldg(g.pts + t);
             const float4 c1 = __ldg(g.pts + (m > 1 ? t + 1 : t));
             const float4 c2 = __ldg(g.pts + (m > 2 ? t + 2 : t));
             const float4 c3 = __ldg(g.pts + (m > 3 ? t + 3 : t));
-            const double d0 = kp_d2(qx, qy, qz, (double)c0.x, (double)c0.y, (double)c0.z);
-            const double d1 = kp_d2(qx, qy, qz, (double)c1.x, (double)c1.y, (double)c1.z);
-            const double d2 = kp_d2(qx, qy, qz, (double)c2.x, (double)c2.y, (double)c2.z);
-            const double d3 = kp_d2(qx, qy, qz, (double)c3.x, (double)c3.y, (double)c3.z);
-            offer(d0, __float_as_int(c0.w));
-            if (m > 1) offer(d1, __float_as_int(c1.w));
-            if (m > 2) offer(d2, __float_as_int(c2.w));
-            if (m > 3) offer(d3, __float_as_int(c3.w));
+            const int b0 = hq_bin(hq_d32(me.x, me.y, me.z, c0), G.scale);
+            const int b1 = hq_bin(hq_d32(me.x, me.y, me.z, c1), G.scale);
+            const int b2 = hq_bin(hq_d32(me.x, me.y, me.z, c2), G.scale);
+            const int b3 = hq_bin(hq_d32(me.x, me.y, me.z, c3), G.scale);
+            // (shared-memory atomics were measured here: 4x slower than the plain read-modify-write)
+            if ((unsigned)b0 < (unsigned)NB) hist[b0 * HQ_THREADS]++;
+            if (m > 1 && (unsigned)b1 < (unsigned)NB) hist[b1 * HQ_THREADS]++;
+            if (m > 2 && (unsigned)b2 < (unsigned)NB) hist[b2 * HQ_THREADS]++;
+            if (m > 3 && (unsigned)b3 < (unsigned)NB) hist[b3 * HQ_THREADS]++;
         }
     }
-    // certificate: every point closer than (cell + distance to the nearest face of the own cell) was seen
-    if (!capped || p.r2cap > g.cell * g.cell * shrink * shrink) {
-        double mg = fmin(fmin(fmin(glo[0], ghi[0]), fmin(glo[1], ghi[1])), fmin(glo[2], ghi[2]));
-        double safe = g.cell * shrink + mg;
-        double s2 = safe * safe;
-        bool exact = (n == k && topd <= s2) || (capped && p.r2cap <= s2);
-        if (!exact) {
-            p.strag_flags[q] = 1;   // flag, not append: the list is compacted in query order so that the
-            return;                 // next level's warps again hold spatial neighbours
-        }
+    // ---- the bin that holds the k-th distance; the histogram becomes the scatter offsets of pass 2
+    int cum = 0, b = -1;
+    for (int j = 0; j < NB; ++j) {
+        const int c = (int)hist[j * HQ_THREADS];
+        hist[j * HQ_THREADS] = (unsigned short)cum;
+        cum += c;
+        if (cum >= k) { b = j; break; }
     }
-    // heapsort in place -> ascending (d2, index)
-    for (int end = n - 1; end > 0; --end) {
-        const double d = hd[end * TQ_THREADS]; const int id = hi[end * TQ_THREADS];
-        hd[end * TQ_THREADS] = hd[0]; hi[end * TQ_THREADS] = hi[0];
-        int pos = 0;
-        for (;;) {
-            int ch = 2 * pos + 1;
-            if (ch >= end) break;
-            double cd = hd[ch * TQ_THREADS]; int ci = hi[ch * TQ_THREADS];
-            if (ch + 1 < end) {
-                double ed = hd[(ch + 1) * TQ_THREADS]; int ei = hi[(ch + 1) * TQ_THREADS];
-                if (tq_greater(ed, ei, cd, ci)) { cd = ed; ci = ei; ++ch; }
+    // fewer than k in range: take them all (the loop ran over every bin, so everything in range is collected)
+    const bool all = !bounded && b < 0;
+    if (b < 0) b = NB - 1;
+    const int m = cum;
+    // (a bin count that wrapped its 16 bits makes m wrong; such a query has > 65535 candidates in one bin and
+    // fails the nput check below)
+    if (m > p.cap || (m < k && !G.cap_binding)) { p.strag_flags[q] = 1; return; }
+    // ---- pass 2: collect bins <= b, counting-sorted by bin.  Cells are chosen by the same rule with a budget
+    // that is never larger than pass 1's, so every collected candidate was counted there.
+    int nput = 0;
+    {
+        const float budget2 = hq_budget(fmin(budget, ((double)b + 1.0) / (double)G.scale));
+        for (int ci = 0; ci < ncols; ++ci) {
+            const int2 rr = hq_column(g, G, HQ_COLS[ci][0], HQ_COLS[ci][1], R, budget2);
+            for (int t = rr.x; t < rr.y; t += 4) {
+                const int mm = rr.y - t;
+                const float4 c0 = __ldg(g.pts + t);
+                const float4 c1 = __ldg(g.pts + (mm > 1 ? t + 1 : t));
+                const float4 c2 = __ldg(g.pts + (mm > 2 ? t + 2 : t));
+                const float4 c3 = __ldg(g.pts + (mm > 3 ? t + 3 : t));
+                const float d0 = hq_d32(me.x, me.y, me.z, c0), d1 = hq_d32(me.x, me.y, me.z, c1);
+                const float d2 = hq_d32(me.x, me.y, me.z, c2), d3 = hq_d32(me.x, me.y, me.z, c3);
+                const int b0 = hq_bin(d0, G.scale), b1 = hq_bin(d1, G.scale), b2 = hq_bin(d2, G.scale), b3 = hq_bin(d3, G.scale);
+#define HQ_PUT(bj, dj, off)                                                                                     \
+    if ((unsigned)(bj) <= (unsigned)b) {                                                                        \
+        const int slot = hist[(bj) * HQ_THREADS];                                                               \
+        hist[(bj) * HQ_THREADS] = (unsigned short)(slot + 1);                                                   \
+        if (slot < m) buf[slot * HQ_THREADS] = ((unsigned long long)__float_as_uint(dj) << 32) | (unsigned)(t + (off)); \
+        ++nput;                                                                                                 \
+    }
+                HQ_PUT(b0, d0, 0)
+                if (mm > 1) HQ_PUT(b1, d1, 1)
+                if (mm > 2) HQ_PUT(b2, d2, 2)
+                if (mm > 3) HQ_PUT(b3, d3, 3)
+#undef HQ_PUT
             }
-            if (!tq_greater(cd, ci, d, id)) break;
-            hd[pos * TQ_THREADS] = cd; hi[pos * TQ_THREADS] = ci;
-            pos = ch;
         }
-        hd[pos * TQ_THREADS] = d; hi[pos * TQ_THREADS] = id;
     }
-    kq_finalize(p, row, n, hd, hi, TQ_THREADS);
+    if (nput != m) { p.strag_flags[q] = 1; return; }   // cannot happen (see above); never trust a scatter blindly
+    // ---- order by (fp32 d2, position): entries only move inside their bin
+    for (int i = 1; i < m; ++i) {
+        const unsigned long long key = buf[i * HQ_THREADS];
+        int j = i - 1;
+        while (j >= 0) {
+            const unsigned long long o = buf[j * HQ_THREADS];
+            if (o <= key) break;
+            buf[(j + 1) * HQ_THREADS] = o;
+            --j;
+        }
+        buf[(j + 1) * HQ_THREADS] = key;
+    }
+    // ---- exact evaluation in that order; the canonical (d2, index) order must be strictly ascending
+    const bool capped = p.r2cap > 0;
+    const bool normals = p.mode == KQ_MODE_NORMALS;
+    double pd = -1.0; int pi = -1;
+    double acc = 0.0;
+    double sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+    bool bad = false, closed = false;
+    for (int i = 0; i < m; ++i) {
+        const float4 c = __ldg(g.pts + (unsigned)buf[i * HQ_THREADS]);
+        const double d = kp_d2(qx, qy, qz, (double)c.x, (double)c.y, (double)c.z);
+        const int id = __float_as_int(c.w);
+        if (!hq_before(pd, pi, d, id)) bad = true;
+        if (capped && !(d < p.r2cap)) closed = true;
+        if (cnt < k && !closed) {
+            pd = d; pi = id;
+            if (normals) {
+                const double x = (double)c.x, y = (double)c.y, z = (double)c.z;
+                sm[0] += x; sm[1] += y; sm[2] += z;
+                sm[3] += x * x; sm[4] += x * y; sm[5] += x * z; sm[6] += y * y; sm[7] += y * z; sm[8] += z * z;
+            } else {
+                if (p.idx) p.idx[row * k + cnt] = id;
+                if (p.d2) p.d2[row * k + cnt] = d;
+                acc = __dadd_rn(acc, sqrt(d));
+            }
+            ++cnt;
+        } else if (closed && d < p.r2cap) bad = true;   // an eligible entry behind an ineligible one: order is off
+    }
+    // exact iff no candidate outside the collected set can precede the k-th entry: the visited-but-uncollected
+    // ones lie above the lower edge of bin b+1, the unvisited ones at or above `budget` (>= that edge)
+    bool exact;
+    if (all && G.cap_binding) exact = true;
+    else exact = cnt == k && pd < hq_lower_edge(b, G.scale) && (G.cap_binding || pd < G.Rcert2);
+    if (bad || !exact) { p.strag_flags[q] = 1; return; }
+    if (normals) { kq_finish_normal(p, row, cnt, sm); return; }
+    if (p.idx) for (int t = cnt; t < k; ++t) p.idx[row * k + t] = -1;
+    if (p.d2) for (int t = cnt; t < k; ++t) p.d2[row * k + t] = INFINITY;
+    if (p.count) p.count[row] = cnt;
+    if (p.mean) p.mean[row] = cnt > 0 ? __ddiv_rn(acc, (double)cnt) : -1.0;
+}
+
+// ---- warp-per-query histogram select: the level-0 stragglers (isolated points and sparse fringes -- what
+// SOR is looking for) against a coarser grid.  Same two passes, but the 27-cell block holds thousands of
+// candidates, so a warp streams it 128 candidates per trip with coalesced 16-byte loads, bins with
+// shared-memory atomics into 512 bins, collects with ballots, and sorts the few survivors once.
+constexpr int WH_WARPS = 4;
+constexpr int WH_NB = 512;
+constexpr int WH_CAP = 128;
+
+__device__ __forceinline__ void wh_sort(unsigned long long *a, int n2, int lane)
+{
+    for (int size = 2; size <= n2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = lane; t < (n2 >> 1); t += 32) {
+                const int i = ((t / stride) * 2 * stride) + (t % stride), j = i + stride;
+                const bool up = (i & size) == 0;
+                const unsigned long long x = a[i], y = a[j];
+                if ((y < x) == up) { a[i] = y; a[j] = x; }
+            }
+            __syncwarp();
+        }
+}
+
+__global__ void __launch_bounds__(WH_WARPS * 32) k_knn_whist(const __grid_constant__ KnnParams p)
+{
+    __shared__ unsigned int s_hist[WH_WARPS][WH_NB];
+    __shared__ unsigned long long s_buf[WH_WARPS][WH_CAP];
+    __shared__ double s_dd[WH_WARPS][WH_CAP];
+    __shared__ int s_ii[WH_WARPS][WH_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const KpGridDev &g = p.g;
+    unsigned int *hist = s_hist[warp];
+    unsigned long long *buf = s_buf[warp];
+    double *dd = s_dd[warp];
+    int *ii = s_ii[warp];
+    const int k = p.k;
+    const int64_t nq = (int64_t)*p.qcount;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int64_t w = (int64_t)blockIdx.x * WH_WARPS + warp; w < nq; w += (int64_t)gridDim.x * WH_WARPS) {
+        const int64_t q = (int64_t)p.qlist[w];
+        const float4 me = __ldg(p.qpts + q);
+        const int64_t row = __float_as_int(me.w);
+        const double qx = (double)me.x, qy = (double)me.y, qz = (double)me.z;
+        HqGeom G;
+        hq_geom(g, qx, qy, qz, p.r2cap, WH_NB, true, 1, G);
+        // the 27 cells, z-rows merged (lanes 0, 3, .., 24 hold one contiguous run each)
+        int a, b;
+        {
+            int2 r = make_int2(0, 0);
+            if (lane < 27) r = kp_cell_range(g, G.cx + lane / 9 - 1, G.cy + (lane / 3) % 3 - 1, G.cz + lane % 3 - 1);
+            const bool ne = r.y > r.x;
+            a = ne ? r.x : 0x7fffffff; b = ne ? r.y : 0;
+            const int a1 = __shfl_down_sync(KP_FULL, a, 1), b1 = __shfl_down_sync(KP_FULL, b, 1);
+            const int a2 = __shfl_down_sync(KP_FULL, a, 2), b2 = __shfl_down_sync(KP_FULL, b, 2);
+            if (lane < 27 && lane % 3 == 0) { a = min(a, min(a1, a2)); b = max(b, max(b1, b2)); if (b == 0) a = 0; }
+            else { a = 0; b = 0; }
+        }
+        const unsigned rows = __ballot_sync(KP_FULL, b > a);
+        for (int j = lane; j < WH_NB; j += 32) hist[j] = 0;
+        __syncwarp();
+        // ---- pass 1
+        for (unsigned mrow = rows; mrow;) {
+            const int j = __ffs(mrow) - 1;
+            mrow &= mrow - 1;
+            const int ra = __shfl_sync(KP_FULL, a, j), rb = __shfl_sync(KP_FULL, b, j);
+            for (int t = ra + lane; t < rb; t += 128) {
+                const float4 c0 = __ldg(g.pts + t);
+                const float4 c1 = __ldg(g.pts + min(t + 32, rb - 1));
+                const float4 c2 = __ldg(g.pts + min(t + 64, rb - 1));
+                const float4 c3 = __ldg(g.pts + min(t + 96, rb - 1));
+                const int b0 = hq_bin(hq_d32(me.x, me.y, me.z, c0), G.scale), b1 = hq_bin(hq_d32(me.x, me.y, me.z, c1), G.scale);
+                const int b2 = hq_bin(hq_d32(me.x, me.y, me.z, c2), G.scale), b3 = hq_bin(hq_d32(me.x, me.y, me.z, c3), G.scale);
+                if ((unsigned)b0 < (unsigned)WH_NB) atomicAdd(hist + b0, 1u);
+                if (t + 32 < rb && (unsigned)b1 < (unsigned)WH_NB) atomicAdd(hist + b1, 1u);
+                if (t + 64 < rb && (unsigned)b2 < (unsigned)WH_NB) atomicAdd(hist + b2, 1u);
+                if (t + 96 < rb && (unsigned)b3 < (unsigned)WH_NB) atomicAdd(hist + b3, 1u);
+            }
+        }
+        __syncwarp();
+        // ---- the bin of the k-th distance: each lane owns 16 consecutive bins
+        int bsel, m, tot;
+        {
+            constexpr int PER = WH_NB / 32;
+            int s = 0;
+            for (int j = 0; j < PER; ++j) s += (int)hist[lane * PER + j];
+            int inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(KP_FULL, inc, o); if (lane >= o) inc += v; }
+            tot = __shfl_sync(KP_FULL, inc, 31);
+            const unsigned reach = __ballot_sync(KP_FULL, inc >= k);
+            int bb = WH_NB - 1, mm = tot;
+            if (reach) {
+                const int L = __ffs(reach) - 1;
+                if (lane == L) {
+                    int cum = inc - s;
+                    for (int j = 0; j < PER; ++j) { cum += (int)hist[lane * PER + j]; if (cum >= k) { bb = lane * PER + j; mm = cum; break; } }
+                }
+                bb = __shfl_sync(KP_FULL, bb, L); mm = __shfl_sync(KP_FULL, mm, L);
+            }
+            bsel = bb; m = mm;
+        }
+        const bool all = (m == tot);
+        bool fail = m > WH_CAP || (m < k && !G.cap_binding);
+        int n = 0;
+        if (!fail) {
+            // ---- pass 2: collect bins <= bsel
+            for (unsigned mrow = rows; mrow;) {
+                const int j = __ffs(mrow) - 1;
+                mrow &= mrow - 1;
+                const int ra = __shfl_sync(KP_FULL, a, j), rb = __shfl_sync(KP_FULL, b, j);
+                for (int t0 = ra; t0 < rb; t0 += 32) {
+                    const int t = t0 + lane;
+                    const bool v = t < rb;
+                    const float4 c = __ldg(g.pts + (v ? t : ra));
+                    const float d = hq_d32(me.x, me.y, me.z, c);
+                    const bool pass = v && (unsigned)hq_bin(d, G.scale) <= (unsigned)bsel;
+                    const unsigned pm = __ballot_sync(KP_FULL, pass);
+                    if (pass) buf[n + __popc(pm & lt)] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)t;
+                    n += __popc(pm);
+                }
+            }
+            int n2 = 32;
+            while (n2 < n) n2 <<= 1;
+            for (int t = n + lane; t < n2; t += 32) buf[t] = ~0ull;
+            __syncwarp();
+            wh_sort(buf, n2, lane);
+            // ---- exact evaluation
+            for (int t = lane; t < n; t += 32) {
+                const float4 c = __ldg(g.pts + (unsigned)buf[t]);
+                dd[t] = kp_d2(qx, qy, qz, (double)c.x, (double)c.y, (double)c.z);
+                ii[t] = __float_as_int(c.w);
+            }
+            __syncwarp();
+            bool bad = false;
+            int within = 0;
+            for (int t = lane; t < n; t += 32) {
+                if (t > 0 && !hq_before(dd[t - 1], ii[t - 1], dd[t], ii[t])) bad = true;
+                if (t < k && (p.r2cap <= 0 || dd[t] < p.r2cap)) ++within;
+            }
+            bad = __any_sync(KP_FULL, bad);
+            const int cnt = kq_warp_sum(within);    // ascending order verified: the eligible entries are a prefix
+            bool exact;
+            if (all && G.cap_binding) exact = true;
+            else exact = cnt == k && dd[k - 1] < hq_lower_edge(bsel, G.scale) && (G.cap_binding || dd[k - 1] < G.Rcert2);
+            fail = bad || !exact;
+            if (!fail && lane == 0) kq_finalize(p, row, cnt, dd, ii, 1);
+        }
+        if (fail && lane == 0) p.strag_flags[q] = 1;
+        __syncwarp();
+    }
 }
 
 int next_pow2(int v)
@@ -803,7 +1104,28 @@ int knn_launch_warp(kp_ctx *ctx, KnnParams &p, int64_t grid_queries)
     return KP_OK;
 }
 
-// d_xyz: the cloud the grid was built from (needed to build the coarser cascade levels; may be NULL)
+template <int NB>
+int knn_launch_hist(kp_ctx *ctx, KnnParams &p)
+{
+    p.cap = p.k + 12;
+    size_t smem = (size_t)HQ_THREADS * ((size_t)p.cap * sizeof(unsigned long long) + (size_t)NB * sizeof(unsigned short));
+    if (smem > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_hist<NB><<<kp_blocks(p.nq, HQ_THREADS), HQ_THREADS, smem, ctx->stream>>>(p);
+    KP_LAUNCH_CHECK(ctx);
+    return KP_OK;
+}
+
+// compacts flags[0..n) (in query order) into list, returns the count on the host (one stream sync)
+int knn_flag_list(kp_ctx *ctx, int64_t n, const uint8_t *flags, int32_t *list, int32_t *d_count, int32_t *h_count)
+{
+    KP_TRY(kp_prim_compact_mask(ctx, n, flags, 0, nullptr, nullptr, list, d_count));
+    KP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, d_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    KP_TRY(kp_fetch_scratch(ctx, sizeof(int32_t)));
+    *h_count = *(int32_t *)ctx->h_scratch;
+    return KP_OK;
+}
+
+// d_xyz: the cloud the grid was built from (needed to build the coarser level; may be NULL)
 int knn_launch(kp_ctx *ctx, KnnParams &p, const char *name, const float *d_xyz = nullptr)
 {
     if (p.nq <= 0) return KP_OK;
@@ -813,45 +1135,40 @@ int knn_launch(kp_ctx *ctx, KnnParams &p, const char *name, const float *d_xyz =
     KP_PROFB(ctx, name, (double)p.g.npts * 16.0 + (double)p.nq * (out_b + (p.queries ? 12.0 : 0.0)));
     p.qlist = nullptr; p.qcount = nullptr; p.strag_flags = nullptr;
     p.qpts = p.g.pts;
-    const bool fast = !p.queries && p.mode != KQ_MODE_RADIUS && p.k <= TQ_KMAX;
+    const bool fast = !p.queries && p.mode != KQ_MODE_RADIUS && p.k <= HQ_KMAX;
     if (!fast) return knn_launch_warp(ctx, p, p.nq);
     const KpGridDev g0 = p.g;
     const int64_t nq0 = p.nq;
-    int32_t *listA, *counts;
+    int32_t *listA, *listB, *counts;
     uint8_t *flags;
     KP_TRY(kp_ws(ctx, (size_t)nq0, &listA));
     KP_TRY(kp_ws(ctx, (size_t)nq0, &flags));
     KP_TRY(kp_ws(ctx, 8, &counts));
     KP_CUDA(ctx, cudaMemsetAsync(counts, 0, 8 * sizeof(int32_t), ctx->stream));
     KP_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)nq0, ctx->stream));
-    size_t smem = (size_t)p.k * TQ_THREADS * (sizeof(double) + sizeof(int));
-    if (smem > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_tq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // level 0: every query against the caller's grid
+    // level 0: every query, one thread each, against the caller's grid
     p.strag_flags = flags;
     {
-        KP_PROF(ctx, "knn_level0");
-        k_knn_tq<<<kp_blocks(nq0, TQ_THREADS), TQ_THREADS, smem, ctx->stream>>>(p);
-        KP_LAUNCH_CHECK(ctx);
+        KP_PROFB(ctx, "knn_level0", (double)p.g.npts * 16.0 + (double)p.nq * out_b);
+        if (p.k <= 32) KP_TRY(knn_launch_hist<32>(ctx, p));
+        else KP_TRY(knn_launch_hist<64>(ctx, p));
     }
-    // A radius-capped search on a grid whose cell covers the radius is always certified: nothing to hand over.
-    const double shrink = 1.0 - 1.0 / 1048576.0;   // same test as the kernel's certificate
-    const bool always_exact = p.r2cap > 0 && !(p.r2cap > g0.cell * g0.cell * shrink * shrink);
-    if (always_exact) return KP_OK;
+    // A radius-capped search on a grid whose cell covers the radius is always certified unless the exact
+    // order is ambiguous in fp32 (ties); the flags still have to be looked at.
     // Queries the 27-cell block could not certify: flying pixels and other isolated points (exactly what SOR is
-    // looking for) plus the sparsest fringes of the cloud.  Their k-th neighbour can be tens of cells away, so
-    // they are finished by the ring-expanding warp kernel on a much COARSER grid (few rings, long contiguous
-    // candidate runs that a warp streams 32 at a time).  The list is compacted in query order.
-    // (sweep in profiles/r01_c_knn_base_coarse_sweep.log: a 4x coarser grid halves the straggler pass for
-    // k = 20; for k = 50 the per-warp buffer sorts dominate and the level-0 grid is as good)
-    const double coarse_mult = getenv("KP_KNN_COARSE_MULT") ? atof(getenv("KP_KNN_COARSE_MULT")) : (p.k <= 32 ? 4.0 : 1.0);
-    KP_TRY(kp_prim_compact_mask(ctx, nq0, flags, 0, nullptr, nullptr, listA, counts));
-    KP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, counts, sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    KP_TRY(kp_fetch_scratch(ctx, sizeof(int32_t)));
-    const int32_t n_strag = *(int32_t *)ctx->h_scratch;
+    // looking for) plus the sparsest fringes of the cloud.  Their k-th neighbour can be many cells away, so
+    // level 1 repeats the selection on a COARSER grid with one warp per query; what even that block cannot
+    // certify goes to the ring-expanding kernel.  Lists are compacted in query order.
+    const double coarse_mult = getenv("KP_KNN_COARSE_MULT") ? atof(getenv("KP_KNN_COARSE_MULT")) : 3.0;
+    int32_t n_strag = 0;
+    KP_TRY(knn_flag_list(ctx, nq0, flags, listA, counts, &n_strag));
     if (getenv("KP_DEBUG_KNN"))
-        fprintf(stderr, "[kp knn] %s k=%d n=%lld cell=%g uncertified=%d\n", name, p.k, (long long)nq0, g0.cell, n_strag);
+        fprintf(stderr, "[kp knn] %s k=%d n=%lld cell=%g level-0 uncertified=%d\n", name, p.k, (long long)nq0, g0.cell, n_strag);
     if (n_strag <= 0) return KP_OK;
-    p.g = g0;
+    p.qpts = g0.pts;
+    p.qlist = listA;
+    p.qcount = counts;
+    p.nq = nq0;
     if (d_xyz && coarse_mult > 1.0) {
         float b6[6];
         for (int c = 0; c < 3; ++c) {
@@ -859,13 +1176,26 @@ int knn_launch(kp_ctx *ctx, KnnParams &p, const char *name, const float *d_xyz =
             b6[3 + c] = (float)(g0.org[c] + g0.cell * (double)g0.dim[c]);
         }
         KpGrid gl;
-        KP_TRY(kp_grid_build(ctx, d_xyz, g0.npts, g0.cell * coarse_mult, b6, &gl));
+        KP_TRY(kp_grid_build(ctx, d_xyz, g0.npts, g0.cell * (double)p.rad * coarse_mult, b6, &gl));
         p.g = kp_grid_dev(gl);
+        KP_TRY(kp_ws(ctx, (size_t)n_strag, &listB));
+        KP_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)nq0, ctx->stream));
+        {
+            KP_PROF(ctx, "knn_level1");
+            int64_t blocks = ((int64_t)n_strag + WH_WARPS - 1) / WH_WARPS;
+            const int64_t cap_blocks = (int64_t)ctx->sm_count * 16;
+            if (blocks > cap_blocks) blocks = cap_blocks;
+            k_knn_whist<<<(unsigned)blocks, WH_WARPS * 32, 0, ctx->stream>>>(p);
+            KP_LAUNCH_CHECK(ctx);
+        }
+        int32_t n2 = 0;
+        KP_TRY(knn_flag_list(ctx, nq0, flags, listB, counts + 1, &n2));
+        if (getenv("KP_DEBUG_KNN")) fprintf(stderr, "[kp knn] %s level-1 cell=%g uncertified=%d\n", name, gl.cell, n2);
+        if (n2 <= 0) return KP_OK;
+        p.qlist = listB;
+        p.qcount = counts + 1;
+        n_strag = n2;
     }
-    p.qpts = g0.pts;
-    p.qlist = listA;
-    p.qcount = counts;
-    p.nq = nq0;
     {
         KP_PROF(ctx, "knn_stragglers");
         return knn_launch_warp(ctx, p, n_strag);
@@ -906,7 +1236,7 @@ int kp_knn_device(kp_ctx *ctx, const KpGrid &g, const float *d_queries, int64_t 
                   double *d_d2, int32_t *d_count, double *d_mean, const float *d_xyz)
 {
     KnnParams p;
-    p.g = kp_grid_dev(g);
+    p.g = kp_grid_dev(g); p.rad = g.rad;
     p.queries = d_queries; p.nq = d_queries ? nq : g.n; p.k = k; p.mode = KQ_MODE_KNN;
     p.r2cap = radius > 0 ? radius * radius : 0.0;
     p.idx = d_idx; p.d2 = d_d2; p.count = d_count; p.mean = d_mean;
@@ -934,14 +1264,14 @@ int kp_sor_device(kp_ctx *ctx, const float *d_xyz, int64_t n, int k, double rati
     double cell = cell_hint;
     if (!(cell > 0.0)) KP_TRY(kp_grid_auto_cell(ctx, d_xyz, n, h_bounds6, 0.5 * k > 4 ? 0.5 * k : 4, &cell));
     KpGrid g;
-    KP_TRY(kp_grid_build(ctx, d_xyz, n, cell, h_bounds6, &g));
+    KP_TRY(kp_grid_build_knn(ctx, d_xyz, n, cell, k, h_bounds6, &g));
     double *mean = d_mean, *tmp, *red;
     if (!mean) KP_TRY(kp_ws(ctx, (size_t)n, &mean));
     KP_TRY(kp_ws(ctx, (size_t)n, &tmp));
     KP_TRY(kp_ws(ctx, (size_t)n / 1024 + (size_t)n / 1048576 + 16, &red));
     {
         KnnParams p;
-        p.g = kp_grid_dev(g);
+        p.g = kp_grid_dev(g); p.rad = g.rad;
         p.queries = nullptr; p.nq = n; p.k = k; p.mode = KQ_MODE_KNN; p.r2cap = 0.0;
         p.idx = nullptr; p.d2 = nullptr; p.count = nullptr; p.mean = mean;
         p.cloud = nullptr; p.normals = nullptr; p.rcount = nullptr;
@@ -975,12 +1305,12 @@ int kp_normals_device(kp_ctx *ctx, const float *d_xyz, int64_t n, double radius,
     if (max_nn < 1) return kp_set_err(ctx, KP_E_ARG, "estimate_normals: max_nn < 1");
     if (n <= 0) return KP_OK;
     double cell;
-    if (radius > 0) cell = radius * (1.0 + 1e-6);
+    if (radius > 0) cell = radius * (1.0 + 4e-6);
     else KP_TRY(kp_grid_auto_cell(ctx, d_xyz, n, h_bounds6, 0.5 * max_nn > 4 ? 0.5 * max_nn : 4, &cell));
     KpGrid g;
-    KP_TRY(kp_grid_build(ctx, d_xyz, n, cell, h_bounds6, &g));
+    KP_TRY(kp_grid_build_knn(ctx, d_xyz, n, cell, max_nn, h_bounds6, &g));
     KnnParams p;
-    p.g = kp_grid_dev(g);
+    p.g = kp_grid_dev(g); p.rad = g.rad;
     p.queries = nullptr; p.nq = n; p.k = max_nn; p.mode = KQ_MODE_NORMALS;
     p.r2cap = radius > 0 ? radius * radius : 0.0;
     p.idx = nullptr; p.d2 = nullptr; p.count = nullptr; p.mean = nullptr;
@@ -1000,11 +1330,12 @@ int kp_knn(kp_ctx *ctx, const float *d_xyz, int64_t n, const float *d_queries, i
     if (nq <= 0) return KP_OK;
     double cell = cell_hint;
     if (!(cell > 0.0)) {
-        if (radius > 0) cell = radius * (1.0 + 1e-6);
+        if (radius > 0) cell = radius * (1.0 + 4e-6);
         else KP_TRY(kp_grid_auto_cell(ctx, d_xyz, n, nullptr, 0.5 * k > 4 ? 0.5 * k : 4, &cell));
     }
     KpGrid g;
-    KP_TRY(kp_grid_build(ctx, d_xyz, n, cell, nullptr, &g));
+    if (d_queries) KP_TRY(kp_grid_build(ctx, d_xyz, n, cell, nullptr, &g));
+    else KP_TRY(kp_grid_build_knn(ctx, d_xyz, n, cell, k, nullptr, &g));
     return kp_knn_device(ctx, g, d_queries, nq, k, radius, d_idx, d_d2, d_count, nullptr, d_xyz);
 }
 
@@ -1029,7 +1360,7 @@ int kp_radius_mask(kp_ctx *ctx, const float *d_xyz, int64_t n, int nb_points, do
     int32_t *cnt = d_counts;
     if (!cnt) KP_TRY(kp_ws(ctx, (size_t)n, &cnt));
     KnnParams p;
-    p.g = kp_grid_dev(g);
+    p.g = kp_grid_dev(g); p.rad = 1;
     p.queries = nullptr; p.nq = n; p.k = 1; p.mode = KQ_MODE_RADIUS; p.r2cap = radius * radius;
     p.idx = nullptr; p.d2 = nullptr; p.count = nullptr; p.mean = nullptr; p.cloud = nullptr; p.normals = nullptr;
     p.rcount = cnt;

@@ -2,13 +2,13 @@
 // Replaces o3d.pipelines.registration.registration_icp(source, target, max_corr, init,
 // TransformationEstimationPointToPlane()) at preprocessing/registration.py:78-84.
 //
-// One kernel launch per pass.  A pass (i) applies the update found by the previous pass to the
+// One kernel launch per pass (k_icp_iter, one thread per source point).  A pass (i) applies the update found by the previous pass to the
 // moving copy of the source (double, in place, like upstream's pcd.Transform(update)),
 // (ii) finds each source point's nearest target point inside max_corr through the target's grid
 // hash (27 cells, z-rows merged, one thread per source point), (iii) accumulates the 21+6+2
-// normal-equation scalars in double per thread, reduces them with warp shuffles, then a
-// shared-memory tree per CTA, then per-CTA slots; (iv) the last CTA to finish (integer ticket)
-// adds the slots in slot order, evaluates fitness / rmse / the convergence test, solves the 6x6
+// normal-equation scalars in double, reduced with warp shuffles (xor butterfly), then a fixed-order
+// sum over the warps of the CTA, then per-CTA slots; (iv) the last CTA to finish (integer ticket)
+// adds the slots in a fixed order, evaluates fitness / rmse / the convergence test, solves the 6x6
 // system, composes T and publishes the next update and a `done` flag.  The host enqueues
 // max_iter+1 passes without reading anything back; passes after `done` return immediately.
 #include <math.h>
@@ -36,6 +36,7 @@ struct IcpParams {
     int32_t *corr;              // [ns] position of the matched target point in g.pts, -1 = none
     int ns;
     double r2;
+    double slack;               // bound on (fp32 d2) - d2 for d2 <= max_corr^2, points near the grid
     int pass, max_iter;
     double rel_fit, rel_rmse;
     IcpState *st;
@@ -78,133 +79,76 @@ __device__ bool icp_solve6(double M[6][7], double *x)
     return true;
 }
 
-// Pass, part 1 (latency-bound, light on registers so many warps stay resident): apply the pending update
-// to the moving source, find each point's nearest target point inside max_corr, store its position.
-__global__ void __launch_bounds__(ICP_THREADS) k_icp_corr(const __grid_constant__ IcpParams p)
+// nearest target point inside max_corr (position in g.pts, -1 = none); `prev` = last pass's partner or -1.
+// Exhaustive and exact in double: a column (or a cell of it) is skipped only when its nearest face is farther
+// than the best match known when the lookups are issued, and the fp32 pre-test only rejects candidates that
+// cannot win (slack bounds the error of the fp32 squared distance: the moving source is double, the test runs
+// on its float rounding).  The cell-map lookups of all needed columns are issued together (branch-free), so
+// their memory round trips overlap instead of queueing behind one another.
+__device__ __forceinline__ int icp_nearest(const KpGridDev &g, double sx, double sy, double sz, double r2, double slack, int prev)
 {
-    const IcpState *st = p.st;
-    if (st->done) return;
-    const KpGridDev &g = p.g;
-    const int i = blockIdx.x * ICP_THREADS + threadIdx.x;
-    if (i >= p.ns) return;
-    double sx = p.cur[3 * (int64_t)i], sy = p.cur[3 * (int64_t)i + 1], sz = p.cur[3 * (int64_t)i + 2];
-    if (p.pass > 0) {
-        const double *U = st->U;
-        double x2 = kp_affine(U[0], U[1], U[2], U[3], sx, sy, sz);
-        double y2 = kp_affine(U[4], U[5], U[6], U[7], sx, sy, sz);
-        double z2 = kp_affine(U[8], U[9], U[10], U[11], sx, sy, sz);
-        sx = x2; sy = y2; sz = z2;
-        p.cur[3 * (int64_t)i] = sx; p.cur[3 * (int64_t)i + 1] = sy; p.cur[3 * (int64_t)i + 2] = sz;
-    }
     int bpos = -1;
-    if (!isnan(sx) && g.dim[0] > 0) {
-        const int cx = kp_cell_coord(g, sx, 0), cy = kp_cell_coord(g, sy, 1), cz = kp_cell_coord(g, sz, 2);
-        double bd = INFINITY;
-        int bi = -1;
-        // Warm start: after the first passes the update is tiny and most points keep their partner.  The
-        // previous partner is a valid candidate, so its distance is an upper bound that lets the row pruning
-        // below skip almost every other row -- the search stays exhaustive (every row that could hold a
-        // closer or equally close point is still scanned), only cheaper.
-        if (p.pass > 0) {
-            const int prev = p.corr[i];
-            if (prev >= 0) {
-                const float4 q = __ldg(g.pts + prev);
-                const double d2 = kp_d2(sx, sy, sz, (double)q.x, (double)q.y, (double)q.z);
-                if (d2 < p.r2) { bd = d2; bi = __float_as_int(q.w); bpos = prev; }
-            }
+    const int cx = kp_cell_coord(g, sx, 0), cy = kp_cell_coord(g, sy, 1), cz = kp_cell_coord(g, sz, 2);
+    double bd = INFINITY;
+    int bi = -1;
+    const float fx32 = (float)sx, fy32 = (float)sy, fz32 = (float)sz;
+    // Warm start: after the first passes the update is tiny and most points keep their partner.  The previous
+    // partner is a valid candidate, so its distance is an upper bound that prunes almost every other cell.
+    if (prev >= 0) {
+        const float4 q = __ldg(g.pts + prev);
+        const double d2 = kp_d2(sx, sy, sz, (double)q.x, (double)q.y, (double)q.z);
+        if (d2 < r2) { bd = d2; bi = __float_as_int(q.w); bpos = prev; }
+    }
+    // fp32 lower bounds of the distances to the faces of the own cell (shrunk, so rounding in the cell
+    // assignment or in the fp32 arithmetic can never hide a closer point)
+    float flo[3], fhi[3];
+    {
+        const double cs = g.cell * (1.0 - 3.0 / 1048576.0);
+        const double ss[3] = {sx, sy, sz};
+        const int cc[3] = {cx, cy, cz};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double f = fmin(fmax((ss[c] - g.org[c]) * g.inv_cell - (double)cc[c], 0.0), 1.0);
+            flo[c] = (float)(f * cs); fhi[c] = (float)((1.0 - f) * cs);
         }
-        // distance to the faces of the own cell (x, y), shrunk a hair so rounding in the cell assignment can
-        // never hide a closer point: a row of cells farther than the best match so far is skipped
-        double glo[2], ghi[2];
-        {
-            const double shrink = 1.0 - 1.0 / 1048576.0;
-            double fx = fmin(fmax((sx - g.org[0]) * g.inv_cell - (double)cx, 0.0), 1.0);
-            double fy = fmin(fmax((sy - g.org[1]) * g.inv_cell - (double)cy, 0.0), 1.0);
-            glo[0] = fx * g.cell * shrink; ghi[0] = (1.0 - fx) * g.cell * shrink;
-            glo[1] = fy * g.cell * shrink; ghi[1] = (1.0 - fy) * g.cell * shrink;
-        }
-        const int order[9] = {4, 1, 3, 5, 7, 0, 2, 6, 8};   // own row first
-        for (int oi = 0; oi < 9; ++oi) {
-            const int dx = order[oi] / 3 - 1, dy = order[oi] % 3 - 1;
-            const double gx = dx < 0 ? glo[0] : (dx > 0 ? ghi[0] : 0.0), gy = dy < 0 ? glo[1] : (dy > 0 ? ghi[1] : 0.0);
-            const double m2 = gx * gx + gy * gy;
-            if (m2 >= p.r2 || m2 > bd) continue;
-            const int2 rr = kp_row_range(g, cx + dx, cy + dy, cz);
-            for (int t = rr.x; t < rr.y; ++t) {
-                float4 q = __ldg(g.pts + t);
-                double d2 = kp_d2(sx, sy, sz, (double)q.x, (double)q.y, (double)q.z);
-                int id = __float_as_int(q.w);
-                if (d2 < p.r2 && (d2 < bd || (d2 == bd && id < bi))) { bd = d2; bi = id; bpos = t; }
+    }
+    const double lim0 = fmin(bd, r2);
+    const float budget = __double2float_ru(lim0 * (1.0 + 4e-6));
+    int2 rng[9];
+#pragma unroll
+    for (int oi = 0; oi < 9; ++oi) {
+        const int dx = oi / 3 - 1, dy = oi % 3 - 1;
+        const float gx = dx < 0 ? flo[0] : (dx > 0 ? fhi[0] : 0.0f), gy = dy < 0 ? flo[1] : (dy > 0 ? fhi[1] : 0.0f);
+        const float zb = budget - (gx * gx + gy * gy);
+        const int zlo = flo[2] * flo[2] <= zb ? cz - 1 : cz, zhi = fhi[2] * fhi[2] <= zb ? cz + 1 : cz;
+        rng[oi] = zb >= 0.0f ? kp_span_range(g, cx + dx, cy + dy, zlo, zhi) : make_int2(0, 0);
+    }
+    float lim32 = __double2float_ru(lim0 + slack), cur = budget;
+    const int order[9] = {4, 1, 3, 5, 7, 0, 2, 6, 8};   // own column first: it tightens the bound for the others
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int oi = order[k], dx = oi / 3 - 1, dy = oi % 3 - 1;
+        const float gx = dx < 0 ? flo[0] : (dx > 0 ? fhi[0] : 0.0f), gy = dy < 0 ? flo[1] : (dy > 0 ? fhi[1] : 0.0f);
+        if (gx * gx + gy * gy > cur) continue;
+        for (int t = rng[oi].x; t < rng[oi].y; ++t) {
+            const float4 q = __ldg(g.pts + t);
+            const float ex = fx32 - q.x, ey = fy32 - q.y, ez = fz32 - q.z;
+            if (__fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex)) > lim32) continue;
+            const double d2 = kp_d2(sx, sy, sz, (double)q.x, (double)q.y, (double)q.z);
+            const int id = __float_as_int(q.w);
+            if (d2 < r2 && (d2 < bd || (d2 == bd && id < bi))) {
+                bd = d2; bi = id; bpos = t;
+                lim32 = __double2float_ru(bd + slack); cur = __double2float_ru(bd * (1.0 + 4e-6));
             }
         }
     }
-    p.corr[i] = bpos;
+    return bpos;
 }
 
-// Pass, part 2 (streaming): accumulate the 29 normal-equation scalars over the matched pairs, reduce, and let
-// the last CTA solve and publish the next update.
-__global__ void __launch_bounds__(ICP_THREADS, 2) k_icp_pass(const __grid_constant__ IcpParams p)
+// last CTA, one thread: fitness / rmse / convergence test, 6x6 solve, next update (kept out of line so its
+// registers do not count against the per-point part of the kernel)
+__device__ __noinline__ void icp_finish(const IcpParams &p, IcpState *st, const double *tot)
 {
-    __shared__ double sh[ICP_THREADS / 32][ICP_NV];
-    __shared__ double tot[ICP_NV];
-    __shared__ unsigned int s_ticket;
-    IcpState *st = p.st;
-    if (st->done) return;
-    const KpGridDev &g = p.g;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    double acc[ICP_NV];
-#pragma unroll
-    for (int i = 0; i < ICP_NV; ++i) acc[i] = 0.0;
-
-    for (int i = blockIdx.x * ICP_THREADS + tid; i < p.ns; i += gridDim.x * ICP_THREADS) {
-        const int bpos = p.corr[i];
-        if (bpos < 0) continue;
-        const double sx = p.cur[3 * (int64_t)i], sy = p.cur[3 * (int64_t)i + 1], sz = p.cur[3 * (int64_t)i + 2];
-        const float4 q = __ldg(g.pts + bpos);
-        const int bi = __float_as_int(q.w);
-        const double ex = sx - (double)q.x, ey = sy - (double)q.y, ez = sz - (double)q.z;
-        const double bd = (ex * ex + ey * ey) + ez * ez;
-        const double nx = (double)p.tgt_normals[3 * (int64_t)bi], ny = (double)p.tgt_normals[3 * (int64_t)bi + 1],
-                     nz = (double)p.tgt_normals[3 * (int64_t)bi + 2];
-        const double r = (ex * nx + ey * ny) + ez * nz;
-        const double J[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
-        int k = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int b = a; b < 6; ++b) acc[k++] += J[a] * J[b];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * r;
-        acc[27] += bd;
-        acc[28] += 1.0;
-    }
-    // warp shuffle reduction, then a fixed-order sum over the warps of the CTA
-#pragma unroll
-    for (int i = 0; i < ICP_NV; ++i) acc[i] = kp_butterfly_sum(acc[i]);
-    if (lane == 0)
-#pragma unroll
-        for (int i = 0; i < ICP_NV; ++i) sh[warp][i] = acc[i];
-    __syncthreads();
-    if (tid < ICP_NV) {
-        double s = 0;
-        for (int w = 0; w < ICP_THREADS / 32; ++w) s += sh[w][tid];
-        p.slots[(size_t)blockIdx.x * ICP_NV + tid] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(&st->ticket, 1u);
-    __syncthreads();
-    if (s_ticket != gridDim.x - 1) return;
-    // ---- last CTA: deterministic cross-CTA sum, solve, update
-    __threadfence();
-    if (tid < ICP_NV) {
-        double s = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(p.slots + (size_t)b * ICP_NV + tid);
-        tot[tid] = s;
-    }
-    __syncthreads();
-    if (tid != 0) return;
     const double nc = tot[28];
     const double fit = p.ns > 0 ? nc / (double)p.ns : 0.0;
     const double rmse = nc > 0 ? sqrt(tot[27] / nc) : 0.0;
@@ -234,14 +178,125 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp_pass(const __grid_consta
         Un[8] = -sb;     Un[9] = cb * sa;                Un[10] = cb * ca;               Un[11] = x[5];
     }
     double Tn[16];
-    for (int i = 0; i < 4; ++i)
+    for (int i2 = 0; i2 < 4; ++i2)
         for (int j = 0; j < 4; ++j) {
             double s = 0;
-            for (int k = 0; k < 4; ++k) s = s + Un[4 * i + k] * st->T[4 * k + j];
-            Tn[4 * i + j] = s;
+            for (int k = 0; k < 4; ++k) s = s + Un[4 * i2 + k] * st->T[4 * k + j];
+            Tn[4 * i2 + j] = s;
         }
-    for (int i = 0; i < 16; ++i) { st->T[i] = Tn[i]; st->U[i] = Un[i]; }
+    for (int i2 = 0; i2 < 16; ++i2) { st->T[i2] = Tn[i2]; st->U[i2] = Un[i2]; }
     __threadfence();
+}
+
+// One pass: update + correspondence + accumulation, one thread per source point; the last CTA solves and
+// publishes the next update.
+__global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_iter(const __grid_constant__ IcpParams p)
+{
+    __shared__ double sh[ICP_THREADS / 32][ICP_NV];
+    __shared__ double part[ICP_THREADS / 32][32];
+    __shared__ double tot[ICP_NV];
+    __shared__ unsigned int s_ticket;
+    IcpState *st = p.st;
+    if (st->done) return;
+    const KpGridDev &g = p.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * ICP_THREADS + tid;
+    bool has = false;
+    double J[6] = {0, 0, 0, 0, 0, 0}, r = 0.0, bd = 0.0;
+    if (i < p.ns) {
+        double sx = p.cur[3 * (int64_t)i], sy = p.cur[3 * (int64_t)i + 1], sz = p.cur[3 * (int64_t)i + 2];
+        int prev = -1;
+        if (p.pass > 0) {
+            const double *U = st->U;
+            const double x2 = kp_affine(U[0], U[1], U[2], U[3], sx, sy, sz);
+            const double y2 = kp_affine(U[4], U[5], U[6], U[7], sx, sy, sz);
+            const double z2 = kp_affine(U[8], U[9], U[10], U[11], sx, sy, sz);
+            sx = x2; sy = y2; sz = z2;
+            p.cur[3 * (int64_t)i] = sx; p.cur[3 * (int64_t)i + 1] = sy; p.cur[3 * (int64_t)i + 2] = sz;
+            prev = p.corr[i];
+        }
+        int bpos = -1;
+        if (!isnan(sx) && g.dim[0] > 0) bpos = icp_nearest(g, sx, sy, sz, p.r2, p.slack, prev);
+        p.corr[i] = bpos;
+        if (bpos >= 0) {
+            has = true;
+            const float4 q = __ldg(g.pts + bpos);
+            const int bi = __float_as_int(q.w);
+            const double ex = sx - (double)q.x, ey = sy - (double)q.y, ez = sz - (double)q.z;
+            bd = (ex * ex + ey * ey) + ez * ez;
+            const double nx = (double)__ldg(p.tgt_normals + 3 * (int64_t)bi), ny = (double)__ldg(p.tgt_normals + 3 * (int64_t)bi + 1),
+                         nz = (double)__ldg(p.tgt_normals + 3 * (int64_t)bi + 2);
+            r = (ex * nx + ey * ny) + ez * nz;
+            J[0] = sy * nz - sz * ny; J[1] = sz * nx - sx * nz; J[2] = sx * ny - sy * nx; J[3] = nx; J[4] = ny; J[5] = nz;
+        }
+    }
+    // Warp reduction of the 29 scalars by halving exchange: at step s a lane keeps one half of its values and
+    // trades the other half with lane^s, so 32 values are fully reduced in 31 exchanges (lane L ends up with
+    // the warp total of value L) instead of 32 butterflies of 5.  Fixed tree -> deterministic.
+    if (__any_sync(KP_FULL, has)) {
+        double v[32];
+        {
+            int k = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = a; b < 6; ++b) v[k++] = J[a] * J[b];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) v[21 + a] = J[a] * r;
+            v[27] = bd; v[28] = has ? 1.0 : 0.0; v[29] = 0.0; v[30] = 0.0; v[31] = 0.0;
+        }
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const bool upper = (lane & s) != 0;
+#pragma unroll
+            for (int j = 0; j < s; ++j) {
+                const double send = upper ? v[j] : v[j + s];
+                const double keep = upper ? v[j + s] : v[j];
+                v[j] = keep + __shfl_xor_sync(KP_FULL, send, s);
+            }
+        }
+        if (lane < ICP_NV) sh[warp][lane] = v[0];
+    } else if (lane < ICP_NV) {
+        sh[warp][lane] = 0.0;
+    }
+    __syncthreads();
+    if (tid < ICP_NV) {
+        double s = 0;
+        for (int w = 0; w < ICP_THREADS / 32; ++w) s += sh[w][tid];
+        p.slots[(size_t)blockIdx.x * ICP_NV + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&st->ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    // ---- last CTA: deterministic cross-CTA sum.  Warp w adds slots w, w+8, ... in order, eight loads in
+    // flight at a time; then the 8 partial sums in order.
+    __threadfence();
+    {
+        double s = 0;
+        if (lane < ICP_NV) {
+            constexpr int W = ICP_THREADS / 32;
+            unsigned b = warp;
+            for (; b + 7 * W < gridDim.x; b += 8 * W) {
+                double t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = __ldcg(p.slots + (size_t)(b + u * W) * ICP_NV + lane);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += t[u];
+            }
+            for (; b < gridDim.x; b += W) s += __ldcg(p.slots + (size_t)b * ICP_NV + lane);
+        }
+        part[warp][lane] = s;
+    }
+    __syncthreads();
+    if (tid < ICP_NV) {
+        double s = 0;
+        for (int w = 0; w < ICP_THREADS / 32; ++w) s += part[w][tid];
+        tot[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) icp_finish(p, st, tot);
 }
 }  // namespace
 
@@ -259,10 +314,18 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
     p.tgt_normals = d_tgt_normals;
     p.ns = (int)n_src;
     p.r2 = max_corr * max_corr;
+    {
+        // fp32 rounding of a coordinate of magnitude <= M costs <= M * 2^-24 per operand; 8 x that covers the
+        // three axes, both operands and the fp32 arithmetic with room to spare
+        double M = 0.0;
+        for (int c = 0; c < 3; ++c)
+            M = fmax(M, fmax(fabs(p.g.org[c]), fabs(p.g.org[c] + p.g.cell * (double)p.g.dim[c])) + 2.0 * max_corr);
+        const double eps = 8.0 * M / 16777216.0;          // bound on |sqrt(fp32 d2) - sqrt(d2)|
+        p.slack = eps * (2.0 * max_corr + eps) * 1.000001 + 4e-6 * p.r2;
+    }
     p.max_iter = max_iter;
     p.rel_fit = rel_fitness; p.rel_rmse = rel_rmse;
-    int grid = (int)kp_blocks(n_src > 0 ? n_src : 1, ICP_THREADS);
-    if (grid > ctx->sm_count * 2) grid = ctx->sm_count * 2;
+    const int grid = (int)kp_blocks(n_src > 0 ? n_src : 1, ICP_THREADS);
     KP_TRY(kp_ws(ctx, (size_t)(n_src > 0 ? n_src : 1) * 3, &p.cur));
     KP_TRY(kp_ws(ctx, (size_t)(n_src > 0 ? n_src : 1), &p.corr));
     KP_TRY(kp_ws(ctx, (size_t)grid * ICP_NV, &p.slots));
@@ -275,9 +338,7 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
     KP_LAUNCH_CHECK(ctx);
     for (int pass = 0; pass <= max_iter; ++pass) {
         p.pass = pass;
-        k_icp_corr<<<kp_blocks(n_src > 0 ? n_src : 1, ICP_THREADS), ICP_THREADS, 0, ctx->stream>>>(p);
-        KP_LAUNCH_CHECK(ctx);
-        k_icp_pass<<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
+        k_icp_iter<<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
         KP_LAUNCH_CHECK(ctx);
     }
     KP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, p.st, sizeof(IcpState), cudaMemcpyDeviceToDevice, ctx->stream));
