@@ -205,7 +205,7 @@ int kp_grid_build(kp_ctx *ctx, const float *d_xyz, int64_t n, double cell, const
 
 int kp_grid_build_knn(kp_ctx *ctx, const float *d_xyz, int64_t n, double cell, int k, const float *h_bounds6, KpGrid *g)
 {
-    static const int want = getenv("KP_KNN_RAD") ? atoi(getenv("KP_KNN_RAD")) : 2;
+    static const int want = getenv("KP_KNN_RAD") ? atoi(getenv("KP_KNN_RAD")) : 1;
     const int rad = (k <= 64 && want == 2) ? 2 : 1;
     KP_TRY(kp_grid_build(ctx, d_xyz, n, cell / (double)rad, h_bounds6, g));
     g->rad = rad;
@@ -771,7 +771,7 @@ __device__ void kq_finish_normal(const KnnParams &p, int64_t row, int cnt, doubl
     p.normals[3 * row] = (float)nr[0]; p.normals[3 * row + 1] = (float)nr[1]; p.normals[3 * row + 2] = (float)nr[2];
 }
 
-template <int NB>
+template <int NB, int R>
 __global__ void __launch_bounds__(HQ_THREADS) k_knn_hist(const __grid_constant__ KnnParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -783,7 +783,7 @@ __global__ void __launch_bounds__(HQ_THREADS) k_knn_hist(const __grid_constant__
     // buf[slot * HQ_THREADS], hist[bin * HQ_THREADS]: any slot pattern is bank-conflict free
     unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem_raw) + tid;
     unsigned short *hist = reinterpret_cast<unsigned short *>(smem_raw + (size_t)p.cap * HQ_THREADS * sizeof(unsigned long long)) + tid;
-    const int k = p.k, R = p.rad;
+    const int k = p.k;
     const float4 me = __ldg(p.qpts + q);
     const int64_t row = __float_as_int(me.w);
     const double qx = (double)me.x, qy = (double)me.y, qz = (double)me.z;
@@ -796,23 +796,8 @@ __global__ void __launch_bounds__(HQ_THREADS) k_knn_hist(const __grid_constant__
     hq_geom(g, qx, qy, qz, p.r2cap, NB, false, R, G);
 #pragma unroll
     for (int j = 0; j < NB; ++j) hist[j * HQ_THREADS] = 0;
-    // ---- pass 1: histogram of the fp32 distances.  Phase A = the 9 inner columns; its histogram bounds the
-    // k-th distance, and phase B (the outer ring, R = 2) only visits the cells that reach inside that bound.
-    // Invariant: every candidate with d2 < budget has been visited.
-    const int ncols = (2 * R + 1) * (2 * R + 1);
-    double budget = G.R2;
-    float fbudget = hq_budget(budget);
-    bool bounded = false;                       // phase A alone reached k
-    for (int ci = 0; ci < ncols; ++ci) {
-        if (ci == 9) {
-            int cum = 0;
-            for (int j = 0; j < NB; ++j) {
-                cum += hist[j * HQ_THREADS];
-                if (cum >= k) { budget = fmin(budget, ((double)j + 1.0) / (double)G.scale); bounded = true; break; }
-            }
-            fbudget = hq_budget(budget);
-        }
-        const int2 rr = hq_column(g, G, HQ_COLS[ci][0], HQ_COLS[ci][1], R, fbudget);
+    // four candidates per trip: the loads and the four distance chains are independent
+    auto count = [&](const int2 rr) {
         for (int t = rr.x; t < rr.y; t += 4) {
             const int m = rr.y - t;
             const float4 c0 = __ldg(g.pts + t);
@@ -829,38 +814,18 @@ __global__ void __launch_bounds__(HQ_THREADS) k_knn_hist(const __grid_constant__
             if (m > 2 && (unsigned)b2 < (unsigned)NB) hist[b2 * HQ_THREADS]++;
             if (m > 3 && (unsigned)b3 < (unsigned)NB) hist[b3 * HQ_THREADS]++;
         }
-    }
-    // ---- the bin that holds the k-th distance; the histogram becomes the scatter offsets of pass 2
-    int cum = 0, b = -1;
-    for (int j = 0; j < NB; ++j) {
-        const int c = (int)hist[j * HQ_THREADS];
-        hist[j * HQ_THREADS] = (unsigned short)cum;
-        cum += c;
-        if (cum >= k) { b = j; break; }
-    }
-    // fewer than k in range: take them all (the loop ran over every bin, so everything in range is collected)
-    const bool all = !bounded && b < 0;
-    if (b < 0) b = NB - 1;
-    const int m = cum;
-    // (a bin count that wrapped its 16 bits makes m wrong; such a query has > 65535 candidates in one bin and
-    // fails the nput check below)
-    if (m > p.cap || (m < k && !G.cap_binding)) { p.strag_flags[q] = 1; return; }
-    // ---- pass 2: collect bins <= b, counting-sorted by bin.  Cells are chosen by the same rule with a budget
-    // that is never larger than pass 1's, so every collected candidate was counted there.
-    int nput = 0;
-    {
-        const float budget2 = hq_budget(fmin(budget, ((double)b + 1.0) / (double)G.scale));
-        for (int ci = 0; ci < ncols; ++ci) {
-            const int2 rr = hq_column(g, G, HQ_COLS[ci][0], HQ_COLS[ci][1], R, budget2);
-            for (int t = rr.x; t < rr.y; t += 4) {
-                const int mm = rr.y - t;
-                const float4 c0 = __ldg(g.pts + t);
-                const float4 c1 = __ldg(g.pts + (mm > 1 ? t + 1 : t));
-                const float4 c2 = __ldg(g.pts + (mm > 2 ? t + 2 : t));
-                const float4 c3 = __ldg(g.pts + (mm > 3 ? t + 3 : t));
-                const float d0 = hq_d32(me.x, me.y, me.z, c0), d1 = hq_d32(me.x, me.y, me.z, c1);
-                const float d2 = hq_d32(me.x, me.y, me.z, c2), d3 = hq_d32(me.x, me.y, me.z, c3);
-                const int b0 = hq_bin(d0, G.scale), b1 = hq_bin(d1, G.scale), b2 = hq_bin(d2, G.scale), b3 = hq_bin(d3, G.scale);
+    };
+    int b = -1, m = 0, nput = 0;
+    auto collect = [&](const int2 rr) {
+        for (int t = rr.x; t < rr.y; t += 4) {
+            const int mm = rr.y - t;
+            const float4 c0 = __ldg(g.pts + t);
+            const float4 c1 = __ldg(g.pts + (mm > 1 ? t + 1 : t));
+            const float4 c2 = __ldg(g.pts + (mm > 2 ? t + 2 : t));
+            const float4 c3 = __ldg(g.pts + (mm > 3 ? t + 3 : t));
+            const float d0 = hq_d32(me.x, me.y, me.z, c0), d1 = hq_d32(me.x, me.y, me.z, c1);
+            const float d2 = hq_d32(me.x, me.y, me.z, c2), d3 = hq_d32(me.x, me.y, me.z, c3);
+            const int b0 = hq_bin(d0, G.scale), b1 = hq_bin(d1, G.scale), b2 = hq_bin(d2, G.scale), b3 = hq_bin(d3, G.scale);
 #define HQ_PUT(bj, dj, off)                                                                                     \
     if ((unsigned)(bj) <= (unsigned)b) {                                                                        \
         const int slot = hist[(bj) * HQ_THREADS];                                                               \
@@ -868,15 +833,75 @@ __global__ void __launch_bounds__(HQ_THREADS) k_knn_hist(const __grid_constant__
         if (slot < m) buf[slot * HQ_THREADS] = ((unsigned long long)__float_as_uint(dj) << 32) | (unsigned)(t + (off)); \
         ++nput;                                                                                                 \
     }
-                HQ_PUT(b0, d0, 0)
-                if (mm > 1) HQ_PUT(b1, d1, 1)
-                if (mm > 2) HQ_PUT(b2, d2, 2)
-                if (mm > 3) HQ_PUT(b3, d3, 3)
+            HQ_PUT(b0, d0, 0)
+            if (mm > 1) HQ_PUT(b1, d1, 1)
+            if (mm > 2) HQ_PUT(b2, d2, 2)
+            if (mm > 3) HQ_PUT(b3, d3, 3)
 #undef HQ_PUT
-            }
         }
+    };
+    // the bin that holds the k-th distance; the histogram becomes the scatter offsets of pass 2
+    auto select_bin = [&]() {
+        int cum = 0;
+        for (int j = 0; j < NB; ++j) {
+            const int c = (int)hist[j * HQ_THREADS];
+            hist[j * HQ_THREADS] = (unsigned short)cum;
+            cum += c;
+            if (cum >= k) { b = j; break; }
+        }
+        m = cum;
+    };
+    // Pass 1 histograms the fp32 distances, pass 2 collects bins <= b counting-sorted by bin.  Invariant:
+    // every candidate with d2 < budget has been visited by pass 1; pass 2 chooses cells by the same rule with
+    // a budget that is never larger, so every collected candidate was counted.
+    double budget = G.R2;
+    bool bounded = false;                       // pass 1 stopped visiting cells beyond a bound found on the way
+    bool all;
+    if constexpr (R == 1) {
+        // 27 cells = 9 columns: ranges stay in registers for pass 2
+        int2 rng[9];
+        const int order[9] = {4, 1, 3, 5, 7, 0, 2, 6, 8};
+        const float fb = hq_budget(budget);
+#pragma unroll
+        for (int ci = 0; ci < 9; ++ci) {
+            rng[ci] = hq_column(g, G, order[ci] / 3 - 1, order[ci] % 3 - 1, 1, fb);
+            count(rng[ci]);
+        }
+        select_bin();
+        all = b < 0;                            // fewer than k in range: the loop ran over every bin, take them all
+        if (b < 0) b = NB - 1;
+        if (m > p.cap || (m < k && !G.cap_binding)) { p.strag_flags[q] = 1; return; }
+        const float fb2 = hq_budget(fmin(budget, ((double)b + 1.0) / (double)G.scale));
+#pragma unroll
+        for (int ci = 0; ci < 9; ++ci) {
+            const float gx = hq_gap(G, 0, order[ci] / 3 - 1), gy = hq_gap(G, 1, order[ci] % 3 - 1);
+            if (gx * gx + gy * gy <= fb2) collect(rng[ci]);
+        }
+    } else {
+        // 125 cells = 25 columns.  Phase A = the 9 inner columns; its histogram bounds the k-th distance, and
+        // phase B (the outer ring) only visits the cells that reach inside that bound.
+        constexpr int ncols = (2 * R + 1) * (2 * R + 1);
+        float fbudget = hq_budget(budget);
+        for (int ci = 0; ci < ncols; ++ci) {
+            if (ci == 9) {
+                int cum = 0;
+                for (int j = 0; j < NB; ++j) {
+                    cum += hist[j * HQ_THREADS];
+                    if (cum >= k) { budget = fmin(budget, ((double)j + 1.0) / (double)G.scale); bounded = true; break; }
+                }
+                fbudget = hq_budget(budget);
+            }
+            count(hq_column(g, G, HQ_COLS[ci][0], HQ_COLS[ci][1], R, fbudget));
+        }
+        select_bin();
+        all = !bounded && b < 0;
+        if (b < 0) b = NB - 1;
+        if (m > p.cap || (m < k && !G.cap_binding)) { p.strag_flags[q] = 1; return; }
+        const float budget2 = hq_budget(fmin(budget, ((double)b + 1.0) / (double)G.scale));
+        for (int ci = 0; ci < ncols; ++ci) collect(hq_column(g, G, HQ_COLS[ci][0], HQ_COLS[ci][1], R, budget2));
     }
-    if (nput != m) { p.strag_flags[q] = 1; return; }   // cannot happen (see above); never trust a scatter blindly
+    // (a bin count that wrapped its 16 bits also ends here: > 65535 puts can never equal m <= cap)
+    if (nput != m) { p.strag_flags[q] = 1; return; }
     // ---- order by (fp32 d2, position): entries only move inside their bin
     for (int i = 1; i < m; ++i) {
         const unsigned long long key = buf[i * HQ_THREADS];
@@ -1104,13 +1129,13 @@ int knn_launch_warp(kp_ctx *ctx, KnnParams &p, int64_t grid_queries)
     return KP_OK;
 }
 
-template <int NB>
+template <int NB, int R>
 int knn_launch_hist(kp_ctx *ctx, KnnParams &p)
 {
     p.cap = p.k + 12;
     size_t smem = (size_t)HQ_THREADS * ((size_t)p.cap * sizeof(unsigned long long) + (size_t)NB * sizeof(unsigned short));
-    if (smem > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_hist<NB><<<kp_blocks(p.nq, HQ_THREADS), HQ_THREADS, smem, ctx->stream>>>(p);
+    if (smem > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist<NB, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_hist<NB, R><<<kp_blocks(p.nq, HQ_THREADS), HQ_THREADS, smem, ctx->stream>>>(p);
     KP_LAUNCH_CHECK(ctx);
     return KP_OK;
 }
@@ -1150,8 +1175,13 @@ int knn_launch(kp_ctx *ctx, KnnParams &p, const char *name, const float *d_xyz =
     p.strag_flags = flags;
     {
         KP_PROFB(ctx, "knn_level0", (double)p.g.npts * 16.0 + (double)p.nq * out_b);
-        if (p.k <= 32) KP_TRY(knn_launch_hist<32>(ctx, p));
-        else KP_TRY(knn_launch_hist<64>(ctx, p));
+        if (p.rad == 2) {
+            if (p.k <= 32) KP_TRY((knn_launch_hist<32, 2>(ctx, p)));
+            else KP_TRY((knn_launch_hist<64, 2>(ctx, p)));
+        } else {
+            if (p.k <= 32) KP_TRY((knn_launch_hist<32, 1>(ctx, p)));
+            else KP_TRY((knn_launch_hist<64, 1>(ctx, p)));
+        }
     }
     // A radius-capped search on a grid whose cell covers the radius is always certified unless the exact
     // order is ambiguous in fp32 (ties); the flags still have to be looked at.

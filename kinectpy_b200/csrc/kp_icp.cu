@@ -43,16 +43,38 @@ struct IcpParams {
     double *slots;              // [gridDim.x][ICP_NV]
 };
 
-__global__ void __launch_bounds__(256) k_icp_init(const float *src, int ns, const __grid_constant__ IcpParams p, IcpState init)
+__global__ void __launch_bounds__(256) k_icp_init(const float *src, int ns, const __grid_constant__ IcpParams p, IcpState init,
+                                                  double *out, unsigned long long *keys, int32_t *vals)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *p.st = init;
     if (i >= ns) return;
     const double *T = init.T;
     double X = src[3 * (int64_t)i], Y = src[3 * (int64_t)i + 1], Z = src[3 * (int64_t)i + 2];
-    p.cur[3 * (int64_t)i] = kp_affine(T[0], T[1], T[2], T[3], X, Y, Z);
-    p.cur[3 * (int64_t)i + 1] = kp_affine(T[4], T[5], T[6], T[7], X, Y, Z);
-    p.cur[3 * (int64_t)i + 2] = kp_affine(T[8], T[9], T[10], T[11], X, Y, Z);
+    const double x = kp_affine(T[0], T[1], T[2], T[3], X, Y, Z);
+    const double y = kp_affine(T[4], T[5], T[6], T[7], X, Y, Z);
+    const double z = kp_affine(T[8], T[9], T[10], T[11], X, Y, Z);
+    out[3 * (int64_t)i] = x; out[3 * (int64_t)i + 1] = y; out[3 * (int64_t)i + 2] = z;
+    if (keys) {
+        // key of the target-grid cell the point starts in (clamped; NaN rows last): the passes walk the source
+        // in this order, so the lanes of a warp look up the same few cell-map words and candidate runs
+        const KpGridDev &g = p.g;
+        unsigned long long key = ~0ull >> 1;
+        if (!isnan(x) && g.dim[0] > 0) {
+            const int cx = min(max(kp_cell_coord(g, x, 0), 0), g.dim[0] - 1);
+            const int cy = min(max(kp_cell_coord(g, y, 1), 0), g.dim[1] - 1);
+            const int cz = min(max(kp_cell_coord(g, z, 2), 0), g.dim[2] - 1);
+            key = kp_cell_key(g, cx, cy, cz);
+        }
+        keys[i] = key; vals[i] = i;
+    }
+}
+__global__ void __launch_bounds__(256) k_icp_reorder(const double *in, const int32_t *order, int ns, double *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const int64_t j = order[i];
+    out[3 * (int64_t)i] = in[3 * j]; out[3 * (int64_t)i + 1] = in[3 * j + 1]; out[3 * (int64_t)i + 2] = in[3 * j + 2];
 }
 
 __device__ bool icp_solve6(double M[6][7], double *x)
@@ -334,8 +356,30 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
     memset(&init, 0, sizeof init);
     for (int i = 0; i < 16; ++i) { init.T[i] = h_init16[i]; init.U[i] = (i % 5 == 0) ? 1.0 : 0.0; }
     p.pass = 0;
-    k_icp_init<<<kp_blocks(n_src > 0 ? n_src : 1, 256), 256, 0, ctx->stream>>>(d_src, (int)n_src, p, init);
-    KP_LAUNCH_CHECK(ctx);
+    {
+        // moving source = init * src, re-ordered by target-grid cell (the normal equations are sums: order-free)
+        const size_t nn = (size_t)(n_src > 0 ? n_src : 1);
+        double *tmp;
+        unsigned long long *keys, *keys_tmp, *keys_sorted;
+        int32_t *vals, *vals_tmp, *vals_sorted;
+        KP_TRY(kp_ws(ctx, nn * 3, &tmp));
+        KP_TRY(kp_ws(ctx, nn, &keys));
+        KP_TRY(kp_ws(ctx, nn, &keys_tmp));
+        KP_TRY(kp_ws(ctx, nn, &vals));
+        KP_TRY(kp_ws(ctx, nn, &vals_tmp));
+        const bool reorder = n_src > 1024 && tgt_grid.n > 0;
+        k_icp_init<<<kp_blocks(nn, 256), 256, 0, ctx->stream>>>(d_src, (int)n_src, p, init, reorder ? tmp : p.cur,
+                                                              reorder ? keys : nullptr, vals);
+        KP_LAUNCH_CHECK(ctx);
+        if (reorder) {
+            int bits = 1;
+            while (bits < 63 && (((unsigned long long)(p.g.dim[0] - 1) << p.g.sh_x) >> bits) != 0ull) ++bits;
+            KP_TRY(kp_prim_sort_pairs_u64(ctx, n_src, bits + 1 > 63 ? 63 : bits + 1, (uint64_t *)keys, (uint64_t *)keys_tmp, vals, vals_tmp,
+                                          (uint64_t **)&keys_sorted, &vals_sorted));
+            k_icp_reorder<<<kp_blocks(nn, 256), 256, 0, ctx->stream>>>(tmp, vals_sorted, (int)n_src, p.cur);
+            KP_LAUNCH_CHECK(ctx);
+        }
+    }
     for (int pass = 0; pass <= max_iter; ++pass) {
         p.pass = pass;
         k_icp_iter<<<grid, ICP_THREADS, 0, ctx->stream>>>(p);

@@ -37,8 +37,8 @@ if __name__ == "__main__":
     else:
         cfgs = []
         for k in (20, 50):
-            for rad in (1, 2):
-                for base in (1.5, 1.8):
+            for rad in (1,):
+                for base in (1.5,):
                     cfgs.append(dict(SW_K=k, SW_BASE=base, KP_KNN_RAD=rad))
         for c in cfgs:
             env = dict(os.environ, KP_DEBUG_KNN="1", **{a: str(b) for a, b in c.items()})
