@@ -217,6 +217,47 @@ KP_EXPORT int kp_icp_point_to_plane(kp_ctx *ctx, const float *d_src, int64_t n_s
                                     double rel_rmse, double *h_T_out, double *h_fitness,
                                     double *h_rmse, int *h_iters, int64_t *h_ncorr);
 
+/* registration_icp(..., TransformationEstimationPointToPoint()) at
+ * manual_pointcloud_registration.py:90-98: same loop, the update is Eigen::umeyama (no scaling) over
+ * the correspondences. */
+KP_EXPORT int kp_icp_point_to_point(kp_ctx *ctx, const float *d_src, int64_t n_src, const float *d_tgt,
+                                    int64_t n_tgt, double max_corr, const double *h_init16, int max_iter,
+                                    double rel_fitness, double rel_rmse, double *h_T_out, double *h_fitness,
+                                    double *h_rmse, int *h_iters, int64_t *h_ncorr);
+/* registration_colored_icp(source, target, max_corr, init, TransformationEstimationForColoredICP(),
+ * criteria) at preprocessing/registration.py:108-113: the target's tangent-plane colour gradients
+ * (hybrid search, radius 2 * max_corr, 30 nn), then the ICP loop with one geometric and one
+ * photometric row per correspondence, weights sqrt(lambda) / sqrt(1 - lambda) (Open3D default 0.968).
+ * Colours are float32 [n][3] in [0, 1]. */
+KP_EXPORT int kp_icp_colored(kp_ctx *ctx, const float *d_src, const float *d_src_colors, int64_t n_src,
+                             const float *d_tgt, const float *d_tgt_colors, const float *d_tgt_normals,
+                             int64_t n_tgt, double max_corr, double lambda_geometric, const double *h_init16,
+                             int max_iter, double rel_fitness, double rel_rmse, double *h_T_out,
+                             double *h_fitness, double *h_rmse, int *h_iters, int64_t *h_ncorr);
+/* the colour gradients alone (d_grad float32 [n][3]); exported for the parity tests */
+KP_EXPORT int kp_color_gradient(kp_ctx *ctx, const float *d_xyz, const float *d_colors, const float *d_normals,
+                                int64_t n, double radius, int max_nn, float *d_grad);
+
+/* ----------------------------------------------------- K6 resample ----- */
+/* Fixed-N resampling feeding PointNet (BASELINE config C5).
+ *   KP_RESAMPLE_RANDOM: select_points_randomly (utils/processing.py:259-275,
+ *     np.random.choice(n, N, replace=False); call site datasets/kinect_dataset.py:103-104).
+ *     The subset is the N points with the smallest (key, index), key =
+ *     min(kp_rng(seed, stream, i) >> 32, 2^32-2), in that order.  N > #valid points
+ *     -> KP_E_ARG (numpy raises ValueError).
+ *   KP_RESAMPLE_PREFIX: points[:N] (datasets/kinect_dataset_npz.py:96-97); h_count = min(n, N).
+ *   d_out float32 [N][3]; d_index_out int32 [N] nullable (RANDOM only). */
+enum { KP_RESAMPLE_RANDOM = 0, KP_RESAMPLE_PREFIX = 1 };
+KP_EXPORT int kp_resample_fixed_n(kp_ctx *ctx, const float *d_xyz, int64_t n, int64_t N, int mode,
+                                  uint64_t seed, uint64_t stream, float *d_out, int32_t *d_index_out,
+                                  int64_t *h_count);
+/* CSR batch: cloud b = rows h_offsets[b] .. h_offsets[b+1] of d_xyz, sample stream first_stream + b;
+ * d_out float32 [B][N][3] (the tensor models/pointnet.py:65 consumes); short PREFIX clouds are
+ * zero-padded; h_counts int64 [B] nullable. */
+KP_EXPORT int kp_resample_batch(kp_ctx *ctx, const float *d_xyz, const int64_t *h_offsets, int B, int64_t N,
+                                int mode, uint64_t seed, uint64_t first_stream, float *d_out,
+                                int64_t *h_counts);
+
 /* ------------------------------------------------ whole-frame driver --- */
 /* Batched driver for BASELINE config C4: per frame unproject -> transform ->
  * fuse -> voxel -> SOR -> floor removal (band + RANSAC + merge + SOR) ->

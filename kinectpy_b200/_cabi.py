@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libkinectpy_b200.so")
 KP_OK, KP_E_ARG, KP_E_CUDA, KP_E_RANGE, KP_E_NOMEM, KP_E_NODEVICE = 0, -1, -2, -3, -4, -5
 UNPROJECT_INT16 = 1
 UNPROJECT_DROP_ANY_ZERO = 2
+RESAMPLE_RANDOM, RESAMPLE_PREFIX = 0, 1
 
 
 class KinectPyB200Error(RuntimeError):
@@ -94,6 +95,13 @@ SIGNATURES = {
     "kp_band_mask": (C.c_int, [_vp, _vp, _i64, C.c_int, _f64, _vp, _pf64, _pi64]),
     "kp_icp_point_to_plane": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _f64, _vp, C.c_int, _f64, _f64, _vp, _pf64, _pf64,
                                         C.POINTER(C.c_int), _pi64]),
+    "kp_icp_point_to_point": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _f64, _vp, C.c_int, _f64, _f64, _vp, _pf64, _pf64,
+                                        C.POINTER(C.c_int), _pi64]),
+    "kp_icp_colored": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _f64, _f64, _vp, C.c_int, _f64, _f64, _vp, _pf64, _pf64,
+                                 C.POINTER(C.c_int), _pi64]),
+    "kp_color_gradient": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f64, C.c_int, _vp]),
+    "kp_resample_fixed_n": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _u64, _u64, _vp, _vp, _pi64]),
+    "kp_resample_batch": (C.c_int, [_vp, _vp, _pi64, C.c_int, _i64, C.c_int, _u64, _u64, _vp, _pi64]),
     "kp_pipeline_create": (C.c_int, [C.c_int, C.POINTER(PipelineCfg), _vp, _vp, C.POINTER(_vp)]),
     "kp_pipeline_destroy": (C.c_int, [_vp]),
     "kp_pipeline_last_error": (C.c_char_p, [_vp]),

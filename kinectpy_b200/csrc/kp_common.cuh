@@ -163,9 +163,21 @@ int kp_ransac_device(kp_ctx *ctx, const float *d_xyz, int64_t n, double thr, int
                      int64_t *d_counts);
 int kp_band_mask_device(kp_ctx *ctx, const float *d_xyz, int64_t n, int axis, double band, uint8_t *d_lower,
                         double *h_axis_max, int64_t *h_nlower);
+// point-to-point / coloured variants of the ICP pass (NULL -> point-to-plane)
+struct KpIcpExtra {
+    int mode = 0;                         // 0 plane, 1 point-to-point, 2 coloured
+    const float *src_colors = nullptr;    // [n_src][3]
+    const float *tgt_intensity = nullptr; // [n_tgt]
+    const float *tgt_grad = nullptr;      // [n_tgt][3]
+    double lambda_geometric = 0.968;
+};
 int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &tgt_grid, const float *d_tgt_normals,
                   double max_corr, const double *h_init16, int max_iter, double rel_fitness, double rel_rmse,
-                  double *h_T_out, double *h_fitness, double *h_rmse, int *h_iters, int64_t *h_ncorr);
+                  double *h_T_out, double *h_fitness, double *h_rmse, int *h_iters, int64_t *h_ncorr,
+                  const KpIcpExtra *extra = nullptr);
+// intensity = (r+g+b)/3 and the tangent-plane colour gradient of every point (coloured ICP target preparation)
+int kp_color_gradient_device(kp_ctx *ctx, const float *d_xyz, const float *d_colors, const float *d_normals, int64_t n,
+                             double radius, int max_nn, float *d_intensity, float *d_grad);
 
 // ------------------------------------------------------- device helpers --
 #ifdef __CUDACC__

@@ -17,7 +17,12 @@
 
 namespace {
 constexpr int ICP_THREADS = 256;
+#ifndef ICP_MIN_CTAS
+#define ICP_MIN_CTAS 4
+#endif
 constexpr int ICP_NV = 29;   // 21 upper-triangular JtJ + 6 Jtr + sum d^2 + count
+                             // (point-to-point: 3 sum s + 3 sum t + 9 sum t s^T in slots 0..14, same two tail slots)
+enum { ICP_PLANE = 0, ICP_POINT = 1, ICP_COLORED = 2 };
 
 struct IcpState {
     double T[16];
@@ -32,6 +37,11 @@ struct IcpState {
 struct IcpParams {
     KpGridDev g;
     const float *tgt_normals;   // indexed by original target index
+    int mode;                   // ICP_PLANE / ICP_POINT / ICP_COLORED
+    const float *src_int;       // colored: source intensity (r+g+b)/3, in the (re-ordered) order of cur
+    const float *tgt_int;       // colored: target intensity, by original target index
+    const float *tgt_grad;      // colored: target colour gradient [nt][3], by original target index
+    double sqrt_lg, sqrt_lp;    // colored: sqrt(lambda_geometric), sqrt(1 - lambda_geometric)
     double *cur;                // [ns][3] moving source
     int32_t *corr;              // [ns] position of the matched target point in g.pts, -1 = none
     int ns;
@@ -167,6 +177,63 @@ __device__ __forceinline__ int icp_nearest(const KpGridDev &g, double sx, double
     return bpos;
 }
 
+// TransformationEstimationPointToPoint::ComputeTransformation = Eigen::umeyama without scaling
+// (manual_pointcloud_registration.py:90-98): R = U diag(1, 1, det(U) det(V)) V^T from the SVD of the
+// cross-covariance, t = mean_t - R mean_s.  The 3x3 SVD is built from the Jacobi eigenvectors of C^T C:
+// with v3 := v1 x v2 and u3 := u1 x u2 both factors are proper rotations and R = [u1 u2 u3][v1 v2 v3]^T is
+// that product for either sign of det C.  tot: sum s (0..2), sum t (3..5), sum t_i s_j (6 + 3 i + j).
+__device__ __noinline__ void icp_umeyama(const double *tot, double n, double *Un)
+{
+    double ms[3], mt[3], Cm[3][3];
+    for (int i = 0; i < 3; ++i) { ms[i] = tot[i] / n; mt[i] = tot[3 + i] / n; }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Cm[i][j] = tot[6 + 3 * i + j] / n - mt[i] * ms[j];
+    // A = C^T C, Jacobi eigen-decomposition (cyclic sweeps)
+    double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double a = 0; for (int k = 0; k < 3; ++k) a += Cm[k][i] * Cm[k][j]; A[i][j] = a; }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off < 1e-300 || off < 1e-22 * (fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]))) break;
+        for (int pq = 0; pq < 3; ++pq) {
+            const int pi = pq == 2 ? 1 : 0, qi = pq == 0 ? 1 : 2;
+            if (A[pi][qi] == 0.0) continue;
+            const double theta = (A[qi][qi] - A[pi][pi]) / (2.0 * A[pi][qi]);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+            for (int k = 0; k < 3; ++k) { const double akp = A[k][pi], akq = A[k][qi]; A[k][pi] = c * akp - sn * akq; A[k][qi] = sn * akp + c * akq; }
+            for (int k = 0; k < 3; ++k) { const double apk = A[pi][k], aqk = A[qi][k]; A[pi][k] = c * apk - sn * aqk; A[qi][k] = sn * apk + c * aqk; }
+            for (int k = 0; k < 3; ++k) { const double vkp = V[k][pi], vkq = V[k][qi]; V[k][pi] = c * vkp - sn * vkq; V[k][qi] = sn * vkp + c * vkq; }
+        }
+    }
+    // order the eigenpairs by descending eigenvalue
+    int o[3] = {0, 1, 2};
+    for (int a = 0; a < 2; ++a) for (int b = a + 1; b < 3; ++b) if (A[o[b]][o[b]] > A[o[a]][o[a]]) { const int t = o[a]; o[a] = o[b]; o[b] = t; }
+    double v1[3], v2[3], v3[3], u1[3], u2[3], u3[3];
+    for (int k = 0; k < 3; ++k) { v1[k] = V[k][o[0]]; v2[k] = V[k][o[1]]; }
+    v3[0] = v1[1] * v2[2] - v1[2] * v2[1]; v3[1] = v1[2] * v2[0] - v1[0] * v2[2]; v3[2] = v1[0] * v2[1] - v1[1] * v2[0];
+    for (int i = 0; i < 3; ++i) { u1[i] = Cm[i][0] * v1[0] + Cm[i][1] * v1[1] + Cm[i][2] * v1[2]; u2[i] = Cm[i][0] * v2[0] + Cm[i][1] * v2[1] + Cm[i][2] * v2[2]; }
+    double l1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    if (!(l1 > 1e-300)) return;                             // zero cross-covariance: keep the identity
+    for (int i = 0; i < 3; ++i) u1[i] /= l1;
+    double d12 = u2[0] * u1[0] + u2[1] * u1[1] + u2[2] * u1[2];
+    for (int i = 0; i < 3; ++i) u2[i] -= d12 * u1[i];
+    double l2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+    if (!(l2 > 1e-12 * l1)) {                               // rank 1: any unit vector orthogonal to u1
+        const int ax = fabs(u1[0]) <= fabs(u1[1]) && fabs(u1[0]) <= fabs(u1[2]) ? 0 : (fabs(u1[1]) <= fabs(u1[2]) ? 1 : 2);
+        double e[3] = {0, 0, 0}; e[ax] = 1.0;
+        const double d = u1[ax];
+        for (int i = 0; i < 3; ++i) u2[i] = e[i] - d * u1[i];
+        l2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+    }
+    for (int i = 0; i < 3; ++i) u2[i] /= l2;
+    u3[0] = u1[1] * u2[2] - u1[2] * u2[1]; u3[1] = u1[2] * u2[0] - u1[0] * u2[2]; u3[2] = u1[0] * u2[1] - u1[1] * u2[0];
+    double Rm[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rm[i][j] = u1[i] * v1[j] + u2[i] * v2[j] + u3[i] * v3[j];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) Un[4 * i + j] = Rm[i][j];
+        Un[4 * i + 3] = mt[i] - (Rm[i][0] * ms[0] + Rm[i][1] * ms[1] + Rm[i][2] * ms[2]);
+    }
+}
+
 // last CTA, one thread: fitness / rmse / convergence test, 6x6 solve, next update (kept out of line so its
 // registers do not count against the per-point part of the kernel)
 __device__ __noinline__ void icp_finish(const IcpParams &p, IcpState *st, const double *tot)
@@ -184,20 +251,24 @@ __device__ __noinline__ void icp_finish(const IcpParams &p, IcpState *st, const 
     }
     if (p.pass == p.max_iter) done = true;
     if (done) { st->done = 1; return; }
-    double M[6][7];
-    {
-        int k = 0;
-        for (int a = 0; a < 6; ++a)
-            for (int b = a; b < 6; ++b) { M[a][b] = tot[k]; M[b][a] = tot[k]; ++k; }
-        for (int a = 0; a < 6; ++a) M[a][6] = -tot[21 + a];
-    }
-    double x[6];
     double Un[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    if (nc > 0 && icp_solve6(M, x)) {
-        double ca = cos(x[0]), sa = sin(x[0]), cb = cos(x[1]), sb = sin(x[1]), cg = cos(x[2]), sg = sin(x[2]);
-        Un[0] = cg * cb; Un[1] = cg * sb * sa - sg * ca; Un[2] = cg * sb * ca + sg * sa; Un[3] = x[3];
-        Un[4] = sg * cb; Un[5] = sg * sb * sa + cg * ca; Un[6] = sg * sb * ca - cg * sa; Un[7] = x[4];
-        Un[8] = -sb;     Un[9] = cb * sa;                Un[10] = cb * ca;               Un[11] = x[5];
+    if (p.mode == ICP_POINT) {
+        if (nc > 0) icp_umeyama(tot, nc, Un);
+    } else {
+        double M[6][7];
+        {
+            int k = 0;
+            for (int a = 0; a < 6; ++a)
+                for (int b = a; b < 6; ++b) { M[a][b] = tot[k]; M[b][a] = tot[k]; ++k; }
+            for (int a = 0; a < 6; ++a) M[a][6] = -tot[21 + a];
+        }
+        double x[6];
+        if (nc > 0 && icp_solve6(M, x)) {
+            double ca = cos(x[0]), sa = sin(x[0]), cb = cos(x[1]), sb = sin(x[1]), cg = cos(x[2]), sg = sin(x[2]);
+            Un[0] = cg * cb; Un[1] = cg * sb * sa - sg * ca; Un[2] = cg * sb * ca + sg * sa; Un[3] = x[3];
+            Un[4] = sg * cb; Un[5] = sg * sb * sa + cg * ca; Un[6] = sg * sb * ca - cg * sa; Un[7] = x[4];
+            Un[8] = -sb;     Un[9] = cb * sa;                Un[10] = cb * ca;               Un[11] = x[5];
+        }
     }
     double Tn[16];
     for (int i2 = 0; i2 < 4; ++i2)
@@ -212,7 +283,8 @@ __device__ __noinline__ void icp_finish(const IcpParams &p, IcpState *st, const 
 
 // One pass: update + correspondence + accumulation, one thread per source point; the last CTA solves and
 // publishes the next update.
-__global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_iter(const __grid_constant__ IcpParams p)
+template <int MODE>
+__global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __grid_constant__ IcpParams p)
 {
     __shared__ double sh[ICP_THREADS / 32][ICP_NV];
     __shared__ double part[ICP_THREADS / 32][32];
@@ -224,7 +296,10 @@ __global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_iter(const __grid_consta
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = blockIdx.x * ICP_THREADS + tid;
     bool has = false;
+    // plane / colored: J (6) and r of the geometric term; colored adds the photometric row J2, r2;
+    // point-to-point: J[0..2] = s, J[3..5] = t
     double J[6] = {0, 0, 0, 0, 0, 0}, r = 0.0, bd = 0.0;
+    double J2[6] = {0, 0, 0, 0, 0, 0}, r2v = 0.0;
     if (i < p.ns) {
         double sx = p.cur[3 * (int64_t)i], sy = p.cur[3 * (int64_t)i + 1], sz = p.cur[3 * (int64_t)i + 2];
         int prev = -1;
@@ -246,10 +321,33 @@ __global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_iter(const __grid_consta
             const int bi = __float_as_int(q.w);
             const double ex = sx - (double)q.x, ey = sy - (double)q.y, ez = sz - (double)q.z;
             bd = (ex * ex + ey * ey) + ez * ez;
-            const double nx = (double)__ldg(p.tgt_normals + 3 * (int64_t)bi), ny = (double)__ldg(p.tgt_normals + 3 * (int64_t)bi + 1),
-                         nz = (double)__ldg(p.tgt_normals + 3 * (int64_t)bi + 2);
-            r = (ex * nx + ey * ny) + ez * nz;
-            J[0] = sy * nz - sz * ny; J[1] = sz * nx - sx * nz; J[2] = sx * ny - sy * nx; J[3] = nx; J[4] = ny; J[5] = nz;
+            if (MODE == ICP_POINT) {
+                J[0] = sx; J[1] = sy; J[2] = sz; J[3] = (double)q.x; J[4] = (double)q.y; J[5] = (double)q.z;
+            } else {
+                const double nx = (double)__ldg(p.tgt_normals + 3 * (int64_t)bi), ny = (double)__ldg(p.tgt_normals + 3 * (int64_t)bi + 1),
+                             nz = (double)__ldg(p.tgt_normals + 3 * (int64_t)bi + 2);
+                r = (ex * nx + ey * ny) + ez * nz;
+                J[0] = sy * nz - sz * ny; J[1] = sz * nx - sx * nz; J[2] = sx * ny - sy * nx; J[3] = nx; J[4] = ny; J[5] = nz;
+                if (MODE == ICP_COLORED) {
+                    // TransformationEstimationForColoredICP (registration.py:108-113): the geometric row weighted
+                    // by sqrt(lambda), plus the photometric row of the colour projected onto the target's tangent plane
+                    const double is = (double)__ldg(p.src_int + i), it = (double)__ldg(p.tgt_int + bi);
+                    const double gx = (double)__ldg(p.tgt_grad + 3 * (int64_t)bi), gy = (double)__ldg(p.tgt_grad + 3 * (int64_t)bi + 1),
+                                 gz = (double)__ldg(p.tgt_grad + 3 * (int64_t)bi + 2);
+                    // vs_proj - vt = e - (e.n) n ;  is_proj = grad.(vs_proj - vt) + it
+                    const double px = ex - r * nx, py = ey - r * ny, pz = ez - r * nz;
+                    const double is_proj = ((gx * px + gy * py) + gz * pz) + it;
+                    // ditM = -(I - n n^T) grad
+                    const double gn = (gx * nx + gy * ny) + gz * nz;
+                    const double mx = -(gx - gn * nx), my = -(gy - gn * ny), mz = -(gz - gn * nz);
+                    J2[0] = p.sqrt_lp * (sy * mz - sz * my); J2[1] = p.sqrt_lp * (sz * mx - sx * mz); J2[2] = p.sqrt_lp * (sx * my - sy * mx);
+                    J2[3] = p.sqrt_lp * mx; J2[4] = p.sqrt_lp * my; J2[5] = p.sqrt_lp * mz;
+                    r2v = p.sqrt_lp * (is - is_proj);
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) J[a] *= p.sqrt_lg;
+                    r *= p.sqrt_lg;
+                }
+            }
         }
     }
     // Warp reduction of the 29 scalars by halving exchange: at step s a lane keeps one half of its values and
@@ -257,16 +355,25 @@ __global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_iter(const __grid_consta
     // the warp total of value L) instead of 32 butterflies of 5.  Fixed tree -> deterministic.
     if (__any_sync(KP_FULL, has)) {
         double v[32];
-        {
+        if (MODE == ICP_POINT) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) v[a] = J[a];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) v[6 + 3 * a + b] = J[3 + a] * J[b];
+#pragma unroll
+            for (int a = 15; a < 27; ++a) v[a] = 0.0;
+        } else {
             int k = 0;
 #pragma unroll
             for (int a = 0; a < 6; ++a)
 #pragma unroll
-                for (int b = a; b < 6; ++b) v[k++] = J[a] * J[b];
+                for (int b = a; b < 6; ++b) { v[k] = J[a] * J[b]; if (MODE == ICP_COLORED) v[k] += J2[a] * J2[b]; ++k; }
 #pragma unroll
-            for (int a = 0; a < 6; ++a) v[21 + a] = J[a] * r;
-            v[27] = bd; v[28] = has ? 1.0 : 0.0; v[29] = 0.0; v[30] = 0.0; v[31] = 0.0;
+            for (int a = 0; a < 6; ++a) { v[21 + a] = J[a] * r; if (MODE == ICP_COLORED) v[21 + a] += J2[a] * r2v; }
         }
+        v[27] = bd; v[28] = has ? 1.0 : 0.0; v[29] = 0.0; v[30] = 0.0; v[31] = 0.0;
 #pragma unroll
         for (int s = 16; s >= 1; s >>= 1) {
             const bool upper = (lane & s) != 0;
@@ -323,9 +430,86 @@ __global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_iter(const __grid_consta
 }  // namespace
 
 // internal form: the target grid is built by the caller (pipeline reuses it for both subs)
+namespace {
+__global__ void __launch_bounds__(256) k_intensity(const float *colors, int64_t n, const int32_t *order, float *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t j = order ? order[i] : i;
+    // (r + g + b) / 3 in double on the float32-stored colours, rounded once
+    out[i] = (float)((((double)colors[3 * j] + (double)colors[3 * j + 1]) + (double)colors[3 * j + 2]) / 3.0);
+}
+
+// InitializePointCloudForColoredICP: per target point, least-squares colour gradient in the tangent plane over
+// its hybrid neighbourhood (rows: projected neighbour offsets -> intensity differences, plus the
+// orthogonality row (nn - 1) n -> 0); fewer than 4 neighbours -> zero gradient.
+__global__ void __launch_bounds__(128) k_color_gradient(const float *xyz, const float *inten, const float *nrm, int64_t n,
+                                                        const int32_t *idx, const int32_t *cnt, int k, float *grad)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int nn = cnt[i];
+    double x[3] = {0, 0, 0};
+    if (nn >= 4 && !isnan(xyz[3 * i])) {
+        const double vx = xyz[3 * i], vy = xyz[3 * i + 1], vz = xyz[3 * i + 2];
+        const double nx = nrm[3 * i], ny = nrm[3 * i + 1], nz = nrm[3 * i + 2];
+        const double it = inten[i];
+        double A[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};   // AtA (xx xy xz yy yz zz), Atb
+        for (int t = 1; t < nn; ++t) {
+            const int64_t j = idx[i * k + t];
+            const double ax = (double)xyz[3 * j] - vx, ay = (double)xyz[3 * j + 1] - vy, az = (double)xyz[3 * j + 2] - vz;
+            const double dn = (ax * nx + ay * ny) + az * nz;
+            const double px = ax - dn * nx, py = ay - dn * ny, pz = az - dn * nz;
+            const double di = (double)inten[j] - it;
+            A[0] += px * px; A[1] += px * py; A[2] += px * pz; A[3] += py * py; A[4] += py * pz; A[5] += pz * pz;
+            b[0] += px * di; b[1] += py * di; b[2] += pz * di;
+        }
+        const double w = (double)(nn - 1);
+        A[0] += w * nx * w * nx; A[1] += w * nx * w * ny; A[2] += w * nx * w * nz;
+        A[3] += w * ny * w * ny; A[4] += w * ny * w * nz; A[5] += w * nz * w * nz;
+        // 3x3 symmetric solve (Gaussian elimination with partial pivoting)
+        double M[3][4] = {{A[0], A[1], A[2], b[0]}, {A[1], A[3], A[4], b[1]}, {A[2], A[4], A[5], b[2]}};
+        bool ok = true;
+        for (int c = 0; c < 3 && ok; ++c) {
+            int pv = c;
+            for (int r2 = c + 1; r2 < 3; ++r2) if (fabs(M[r2][c]) > fabs(M[pv][c])) pv = r2;
+            if (!(fabs(M[pv][c]) > 1e-300)) { ok = false; break; }
+            if (pv != c) for (int j = 0; j < 4; ++j) { const double tv = M[c][j]; M[c][j] = M[pv][j]; M[pv][j] = tv; }
+            for (int r2 = c + 1; r2 < 3; ++r2) { const double f = M[r2][c] / M[c][c]; for (int j = c; j < 4; ++j) M[r2][j] -= f * M[c][j]; }
+        }
+        if (ok) {
+            x[2] = M[2][3] / M[2][2];
+            x[1] = (M[1][3] - M[1][2] * x[2]) / M[1][1];
+            x[0] = (M[0][3] - M[0][1] * x[1] - M[0][2] * x[2]) / M[0][0];
+            if (!(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]))) x[0] = x[1] = x[2] = 0.0;
+        }
+    }
+    grad[3 * i] = (float)x[0]; grad[3 * i + 1] = (float)x[1]; grad[3 * i + 2] = (float)x[2];
+}
+}  // namespace
+
+int kp_color_gradient_device(kp_ctx *ctx, const float *d_xyz, const float *d_colors, const float *d_normals, int64_t n,
+                             double radius, int max_nn, float *d_intensity, float *d_grad)
+{
+    if (n <= 0) return KP_OK;
+    if (max_nn < 1 || !(radius > 0.0)) return kp_set_err(ctx, KP_E_ARG, "colour gradient: radius <= 0 or max_nn < 1");
+    k_intensity<<<kp_blocks(n, 256), 256, 0, ctx->stream>>>(d_colors, n, nullptr, d_intensity);
+    KP_LAUNCH_CHECK(ctx);
+    KpGrid g;
+    KP_TRY(kp_grid_build_knn(ctx, d_xyz, n, radius * (1.0 + 4e-6), max_nn, nullptr, &g));
+    int32_t *idx, *cnt;
+    KP_TRY(kp_ws(ctx, (size_t)n * (size_t)max_nn, &idx));
+    KP_TRY(kp_ws(ctx, (size_t)n, &cnt));
+    KP_TRY(kp_knn_device(ctx, g, nullptr, n, max_nn, radius, idx, nullptr, cnt, nullptr, d_xyz));
+    KP_PROFB(ctx, "color_gradient", (double)n * (4.0 * max_nn + 12.0 + 12.0 + 4.0 + 12.0));
+    k_color_gradient<<<kp_blocks(n, 128), 128, 0, ctx->stream>>>(d_xyz, d_intensity, d_normals, n, idx, cnt, max_nn, d_grad);
+    KP_LAUNCH_CHECK(ctx);
+    return KP_OK;
+}
+
 int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &tgt_grid, const float *d_tgt_normals,
                   double max_corr, const double *h_init16, int max_iter, double rel_fitness, double rel_rmse,
-                  double *h_T_out, double *h_fitness, double *h_rmse, int *h_iters, int64_t *h_ncorr)
+                  double *h_T_out, double *h_fitness, double *h_rmse, int *h_iters, int64_t *h_ncorr, const KpIcpExtra *extra)
 {
     if (n_src > 2147483000LL) return kp_set_err(ctx, KP_E_ARG, "more than 2^31 points in one call");
     if (max_iter < 0) max_iter = 0;
@@ -334,6 +518,10 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
     p.g = kp_grid_dev(tgt_grid);
     if (tgt_grid.n <= 0) p.g.dim[0] = p.g.dim[1] = p.g.dim[2] = 0;
     p.tgt_normals = d_tgt_normals;
+    p.mode = extra ? extra->mode : ICP_PLANE;
+    p.src_int = nullptr; p.tgt_int = extra ? extra->tgt_intensity : nullptr; p.tgt_grad = extra ? extra->tgt_grad : nullptr;
+    const double lg = extra ? extra->lambda_geometric : 1.0;
+    p.sqrt_lg = sqrt(lg); p.sqrt_lp = sqrt(1.0 - lg);
     p.ns = (int)n_src;
     p.r2 = max_corr * max_corr;
     {
@@ -361,7 +549,7 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
         const size_t nn = (size_t)(n_src > 0 ? n_src : 1);
         double *tmp;
         unsigned long long *keys, *keys_tmp, *keys_sorted;
-        int32_t *vals, *vals_tmp, *vals_sorted;
+        int32_t *vals, *vals_tmp, *vals_sorted = nullptr;
         KP_TRY(kp_ws(ctx, nn * 3, &tmp));
         KP_TRY(kp_ws(ctx, nn, &keys));
         KP_TRY(kp_ws(ctx, nn, &keys_tmp));
@@ -379,10 +567,19 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
             k_icp_reorder<<<kp_blocks(nn, 256), 256, 0, ctx->stream>>>(tmp, vals_sorted, (int)n_src, p.cur);
             KP_LAUNCH_CHECK(ctx);
         }
+        if (p.mode == ICP_COLORED && n_src > 0) {
+            float *si;
+            KP_TRY(kp_ws(ctx, nn, &si));
+            k_intensity<<<kp_blocks(nn, 256), 256, 0, ctx->stream>>>(extra->src_colors, n_src, reorder ? vals_sorted : nullptr, si);
+            KP_LAUNCH_CHECK(ctx);
+            p.src_int = si;
+        }
     }
     for (int pass = 0; pass <= max_iter; ++pass) {
         p.pass = pass;
-        k_icp_iter<<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
+        if (p.mode == ICP_POINT) k_icp_iter<ICP_POINT><<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
+        else if (p.mode == ICP_COLORED) k_icp_iter<ICP_COLORED><<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
+        else k_icp_iter<ICP_PLANE><<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
         KP_LAUNCH_CHECK(ctx);
     }
     KP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, p.st, sizeof(IcpState), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -398,10 +595,12 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
     return KP_OK;
 }
 
-extern "C" int kp_icp_point_to_plane(kp_ctx *ctx, const float *d_src, int64_t n_src, const float *d_tgt,
-                                     const float *d_tgt_normals, int64_t n_tgt, double max_corr, const double *h_init16,
-                                     int max_iter, double rel_fitness, double rel_rmse, double *h_T_out,
-                                     double *h_fitness, double *h_rmse, int *h_iters, int64_t *h_ncorr)
+extern "C" {
+
+int kp_icp_point_to_plane(kp_ctx *ctx, const float *d_src, int64_t n_src, const float *d_tgt,
+                          const float *d_tgt_normals, int64_t n_tgt, double max_corr, const double *h_init16,
+                          int max_iter, double rel_fitness, double rel_rmse, double *h_T_out,
+                          double *h_fitness, double *h_rmse, int *h_iters, int64_t *h_ncorr)
 {
     if (!ctx || !h_init16) return kp_set_err(ctx, KP_E_ARG, "kp_icp_point_to_plane: NULL argument");
     if (!(max_corr > 0.0)) return kp_set_err(ctx, KP_E_ARG, "registration_icp: max_correspondence_distance <= 0");
@@ -410,5 +609,57 @@ extern "C" int kp_icp_point_to_plane(kp_ctx *ctx, const float *d_src, int64_t n_
     KpGrid g;
     KP_TRY(kp_grid_build(ctx, d_tgt, n_tgt, max_corr * (1.0 + 1e-6), nullptr, &g));
     return kp_icp_device(ctx, d_src, n_src, g, d_tgt_normals, max_corr, h_init16, max_iter, rel_fitness, rel_rmse, h_T_out,
-                         h_fitness, h_rmse, h_iters, h_ncorr);
+                         h_fitness, h_rmse, h_iters, h_ncorr, nullptr);
 }
+
+int kp_icp_point_to_point(kp_ctx *ctx, const float *d_src, int64_t n_src, const float *d_tgt, int64_t n_tgt,
+                          double max_corr, const double *h_init16, int max_iter, double rel_fitness, double rel_rmse,
+                          double *h_T_out, double *h_fitness, double *h_rmse, int *h_iters, int64_t *h_ncorr)
+{
+    if (!ctx || !h_init16) return kp_set_err(ctx, KP_E_ARG, "kp_icp_point_to_point: NULL argument");
+    if (!(max_corr > 0.0)) return kp_set_err(ctx, KP_E_ARG, "registration_icp: max_correspondence_distance <= 0");
+    kp_enter(ctx);
+    KpGrid g;
+    KP_TRY(kp_grid_build(ctx, d_tgt, n_tgt, max_corr * (1.0 + 1e-6), nullptr, &g));
+    KpIcpExtra ex;
+    ex.mode = ICP_POINT;
+    return kp_icp_device(ctx, d_src, n_src, g, nullptr, max_corr, h_init16, max_iter, rel_fitness, rel_rmse, h_T_out,
+                         h_fitness, h_rmse, h_iters, h_ncorr, &ex);
+}
+
+int kp_color_gradient(kp_ctx *ctx, const float *d_xyz, const float *d_colors, const float *d_normals, int64_t n,
+                      double radius, int max_nn, float *d_grad)
+{
+    if (!ctx || (n > 0 && (!d_xyz || !d_colors || !d_normals || !d_grad))) return kp_set_err(ctx, KP_E_ARG, "kp_color_gradient: NULL argument");
+    kp_enter(ctx);
+    float *inten;
+    KP_TRY(kp_ws(ctx, (size_t)(n > 0 ? n : 1), &inten));
+    return kp_color_gradient_device(ctx, d_xyz, d_colors, d_normals, n, radius, max_nn, inten, d_grad);
+}
+
+int kp_icp_colored(kp_ctx *ctx, const float *d_src, const float *d_src_colors, int64_t n_src, const float *d_tgt,
+                   const float *d_tgt_colors, const float *d_tgt_normals, int64_t n_tgt, double max_corr,
+                   double lambda_geometric, const double *h_init16, int max_iter, double rel_fitness, double rel_rmse,
+                   double *h_T_out, double *h_fitness, double *h_rmse, int *h_iters, int64_t *h_ncorr)
+{
+    if (!ctx || !h_init16) return kp_set_err(ctx, KP_E_ARG, "kp_icp_colored: NULL argument");
+    if (!(max_corr > 0.0)) return kp_set_err(ctx, KP_E_ARG, "registration_colored_icp: max_correspondence_distance <= 0");
+    if (!d_tgt_normals || !d_tgt_colors || !d_src_colors)
+        return kp_set_err(ctx, KP_E_ARG, "registration_colored_icp requires source colours and target colours + normals");
+    if (!(lambda_geometric >= 0.0 && lambda_geometric <= 1.0)) return kp_set_err(ctx, KP_E_ARG, "lambda_geometric outside [0, 1]");
+    kp_enter(ctx);
+    float *inten, *grad;
+    KP_TRY(kp_ws(ctx, (size_t)(n_tgt > 0 ? n_tgt : 1), &inten));
+    KP_TRY(kp_ws(ctx, (size_t)(n_tgt > 0 ? n_tgt : 1) * 3, &grad));
+    // InitializePointCloudForColoredICP(target, KDTreeSearchParamHybrid(2 * max_distance, 30))
+    KP_TRY(kp_color_gradient_device(ctx, d_tgt, d_tgt_colors, d_tgt_normals, n_tgt, 2.0 * max_corr, 30, inten, grad));
+    KpGrid g;
+    KP_TRY(kp_grid_build(ctx, d_tgt, n_tgt, max_corr * (1.0 + 1e-6), nullptr, &g));
+    KpIcpExtra ex;
+    ex.mode = ICP_COLORED; ex.src_colors = d_src_colors; ex.tgt_intensity = inten; ex.tgt_grad = grad;
+    ex.lambda_geometric = lambda_geometric;
+    return kp_icp_device(ctx, d_src, n_src, g, d_tgt_normals, max_corr, h_init16, max_iter, rel_fitness, rel_rmse, h_T_out,
+                         h_fitness, h_rmse, h_iters, h_ncorr, &ex);
+}
+
+}  // extern "C"

@@ -394,7 +394,37 @@ class TransformationEstimationPointToPlane:
 
 class TransformationEstimationPointToPoint:
     def __init__(self, with_scaling: bool = False):
+        if with_scaling:
+            raise NotImplementedError("with_scaling=True is not used by the reference")
         self.with_scaling = with_scaling
+
+    def compute_transformation(self, source: "PointCloud", target: "PointCloud", corres) -> np.ndarray:
+        """``p2p.compute_transformation(source, target, Vector2iVector(corr))`` at
+        ``manual_pointcloud_registration.py:90-92``: Umeyama / Kabsch over a handful of hand-picked pairs
+        (host-side; three to a dozen points are not device work)."""
+        c = np.asarray(corres).astype(np.int64).reshape(-1, 2)
+        s = np.asarray(source.points, dtype=np.float64)[c[:, 0]]
+        t = np.asarray(target.points, dtype=np.float64)[c[:, 1]]
+        T = np.eye(4)
+        if len(c) == 0:
+            return T
+        ms, mt = s.mean(axis=0), t.mean(axis=0)
+        cov = (t - mt).T @ (s - ms) / len(c)
+        U, _, Vt = np.linalg.svd(cov)
+        S = np.diag([1.0, 1.0, -1.0 if np.linalg.det(U) * np.linalg.det(Vt) < 0 else 1.0])
+        R = U @ S @ Vt
+        T[:3, :3] = R
+        T[:3, 3] = mt - R @ ms
+        return T
+
+
+class TransformationEstimationForColoredICP:
+    def __init__(self, lambda_geometric: float = 0.968):
+        self.lambda_geometric = float(lambda_geometric)
+
+
+def Vector2iVector(a) -> np.ndarray:
+    return np.asarray(a).astype(np.int32).reshape(-1, 2)
 
 
 class ICPConvergenceCriteria:
@@ -415,25 +445,63 @@ class RegistrationResult:
                 f"and correspondence_set size of {self.num_correspondences}")
 
 
+def _icp_outputs():
+    return np.zeros(16, dtype=np.float64), C.c_double(), C.c_double(), C.c_int(), C.c_int64()
+
+
 def registration_icp(source: PointCloud, target: PointCloud, max_correspondence_distance: float, init=None,
                      estimation_method=None, criteria: Optional[ICPConvergenceCriteria] = None) -> RegistrationResult:
-    """``o3d.pipelines.registration.registration_icp`` for point-to-plane (registration.py:78-84)."""
-    if estimation_method is not None and not isinstance(estimation_method, TransformationEstimationPointToPlane):
-        raise NotImplementedError("only TransformationEstimationPointToPlane is on the B200 path (SURVEY.md 8f: f4)")
+    """``o3d.pipelines.registration.registration_icp``: point-to-plane (``registration.py:78-84``) and
+    point-to-point (``manual_pointcloud_registration.py:94-98``; Open3D's default estimator)."""
+    if estimation_method is None:
+        estimation_method = TransformationEstimationPointToPoint()
+    if isinstance(estimation_method, TransformationEstimationForColoredICP):
+        return registration_colored_icp(source, target, max_correspondence_distance, init, estimation_method, criteria)
     if not max_correspondence_distance > 0:
         raise KinectPyB200Error(_cabi.KP_E_ARG, "max_correspondence_distance <= 0")
-    if not target.has_normals():
-        raise KinectPyB200Error(_cabi.KP_E_ARG, "TransformationEstimationPointToPlane requires target normals")
     crit = criteria or ICPConvergenceCriteria()
     ctx = source._ctx
     _, s_pts, _, _ = source._dev()
     _, t_pts, _, t_nrm = target._dev()
     T0 = _cabi.T16(np.eye(4) if init is None else init)
-    T = np.zeros(16, dtype=np.float64)
-    fit, rmse, iters, nc = C.c_double(), C.c_double(), C.c_int(), C.c_int64()
-    ctx.check(ctx.lib.kp_icp_point_to_plane(ctx.handle, PointCloud._ptr(s_pts), len(source), PointCloud._ptr(t_pts),
-                                            PointCloud._ptr(t_nrm), len(target), float(max_correspondence_distance),
-                                            T0.ctypes.data, int(crit.max_iteration), float(crit.relative_fitness),
-                                            float(crit.relative_rmse), T.ctypes.data, C.byref(fit), C.byref(rmse),
-                                            C.byref(iters), C.byref(nc)))
+    T, fit, rmse, iters, nc = _icp_outputs()
+    if isinstance(estimation_method, TransformationEstimationPointToPlane):
+        if not target.has_normals():
+            raise KinectPyB200Error(_cabi.KP_E_ARG, "TransformationEstimationPointToPlane requires target normals")
+        ctx.check(ctx.lib.kp_icp_point_to_plane(ctx.handle, PointCloud._ptr(s_pts), len(source), PointCloud._ptr(t_pts),
+                                                PointCloud._ptr(t_nrm), len(target), float(max_correspondence_distance),
+                                                T0.ctypes.data, int(crit.max_iteration), float(crit.relative_fitness),
+                                                float(crit.relative_rmse), T.ctypes.data, C.byref(fit), C.byref(rmse),
+                                                C.byref(iters), C.byref(nc)))
+    elif isinstance(estimation_method, TransformationEstimationPointToPoint):
+        ctx.check(ctx.lib.kp_icp_point_to_point(ctx.handle, PointCloud._ptr(s_pts), len(source), PointCloud._ptr(t_pts),
+                                                len(target), float(max_correspondence_distance), T0.ctypes.data,
+                                                int(crit.max_iteration), float(crit.relative_fitness),
+                                                float(crit.relative_rmse), T.ctypes.data, C.byref(fit), C.byref(rmse),
+                                                C.byref(iters), C.byref(nc)))
+    else:
+        raise TypeError("unknown estimation method %r" % (estimation_method,))
+    return RegistrationResult(T.reshape(4, 4).copy(), fit.value, rmse.value, iters.value, nc.value)
+
+
+def registration_colored_icp(source: PointCloud, target: PointCloud, max_correspondence_distance: float, init=None,
+                             estimation_method: Optional[TransformationEstimationForColoredICP] = None,
+                             criteria: Optional[ICPConvergenceCriteria] = None) -> RegistrationResult:
+    """``o3d.pipelines.registration.registration_colored_icp`` (``registration.py:108-113``)."""
+    est = estimation_method or TransformationEstimationForColoredICP()
+    if not max_correspondence_distance > 0:
+        raise KinectPyB200Error(_cabi.KP_E_ARG, "max_correspondence_distance <= 0")
+    if not (source.has_colors() and target.has_colors() and target.has_normals()):
+        raise KinectPyB200Error(_cabi.KP_E_ARG, "ColoredICP requires source colours and target colours + normals")
+    crit = criteria or ICPConvergenceCriteria()
+    ctx = source._ctx
+    _, s_pts, s_col, _ = source._dev()
+    _, t_pts, t_col, t_nrm = target._dev()
+    T0 = _cabi.T16(np.eye(4) if init is None else init)
+    T, fit, rmse, iters, nc = _icp_outputs()
+    ctx.check(ctx.lib.kp_icp_colored(ctx.handle, PointCloud._ptr(s_pts), PointCloud._ptr(s_col), len(source),
+                                     PointCloud._ptr(t_pts), PointCloud._ptr(t_col), PointCloud._ptr(t_nrm), len(target),
+                                     float(max_correspondence_distance), est.lambda_geometric, T0.ctypes.data,
+                                     int(crit.max_iteration), float(crit.relative_fitness), float(crit.relative_rmse),
+                                     T.ctypes.data, C.byref(fit), C.byref(rmse), C.byref(iters), C.byref(nc)))
     return RegistrationResult(T.reshape(4, 4).copy(), fit.value, rmse.value, iters.value, nc.value)

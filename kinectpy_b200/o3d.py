@@ -19,7 +19,7 @@ geometry = SimpleNamespace(
     KDTreeSearchParamHybrid=_g.KDTreeSearchParamHybrid,
     KDTreeSearchParamKNN=_g.KDTreeSearchParamKNN,
 )
-utility = SimpleNamespace(Vector3dVector=_g.Vector3dVector, random=SimpleNamespace(seed=_g.seed))
+utility = SimpleNamespace(Vector3dVector=_g.Vector3dVector, Vector2iVector=_g.Vector2iVector, random=SimpleNamespace(seed=_g.seed))
 pipelines = SimpleNamespace(registration=SimpleNamespace(
     registration_icp=_g.registration_icp,
     TransformationEstimationPointToPlane=_g.TransformationEstimationPointToPlane,
@@ -28,6 +28,7 @@ pipelines = SimpleNamespace(registration=SimpleNamespace(
     RegistrationResult=_g.RegistrationResult,
     compute_fpfh_feature=_not_on_path("compute_fpfh_feature"),
     registration_ransac_based_on_feature_matching=_not_on_path("registration_ransac_based_on_feature_matching"),
-    registration_colored_icp=_not_on_path("registration_colored_icp"),
+    registration_colored_icp=_g.registration_colored_icp,
+    TransformationEstimationForColoredICP=_g.TransformationEstimationForColoredICP,
 ))
 io = SimpleNamespace(read_point_cloud=_io.read_point_cloud, write_point_cloud=_io.write_point_cloud)

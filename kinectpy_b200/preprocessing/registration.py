@@ -1,8 +1,7 @@
 """B200 counterpart of the reference's ``preprocessing/registration.py``.
 
 Same function names, argument order and defaults.  The voxel downsample, normal estimation and the
-whole point-to-plane ICP loop run on the GPU.  FPFH features, feature-matching global registration
-and coloured ICP are the "next" rows of SURVEY.md section 8f and raise ``NotImplementedError``.
+whole ICP loop (point-to-plane, point-to-point, coloured) run on the GPU.
 
 Roles, as in the reference: ``prepare_dataset`` makes the *sub* cloud the ICP source and the
 *master* cloud the target (``registration.py:25-26``), so the returned 4x4 maps sub coordinates
@@ -59,5 +58,20 @@ def execute_point_to_plane_registration(pcd_master, pcd_sub, initial_transformat
     return result if return_result else result.transformation
 
 
-def execute_colored_ICP_registration(pcd_master, pcd_sub, initial_transformation):
-    raise NotImplementedError("coloured ICP is a 'next' row (SURVEY.md section 8f, f4)")
+def execute_colored_ICP_registration(pcd_master, pcd_sub, initial_transformation,
+                                     voxel_radius=(80, 40, 20), max_iter=(50, 30, 14)):
+    """Multi-scale coloured ICP (``registration.py:89-114``).  Restated as written: source <- master,
+    target <- sub (``:92-93``), every scale starts again from ``initial_transformation`` (the reference
+    never feeds a scale's result into the next), and the last scale's transform is
+    returned.  ``voxel_radius`` / ``max_iter`` are the literals of ``:95-96`` exposed as keywords."""
+    source, target = copy.deepcopy(pcd_master), copy.deepcopy(pcd_sub)
+    result_icp = None
+    for radius, iters in zip(voxel_radius, max_iter):
+        source_down = source.voxel_down_sample(radius)
+        target_down = target.voxel_down_sample(radius)
+        source_down.estimate_normals(_g.KDTreeSearchParamHybrid(radius=radius * 2, max_nn=30))
+        target_down.estimate_normals(_g.KDTreeSearchParamHybrid(radius=radius * 2, max_nn=30))
+        result_icp = _g.registration_colored_icp(
+            source_down, target_down, radius, initial_transformation, _g.TransformationEstimationForColoredICP(),
+            _g.ICPConvergenceCriteria(relative_fitness=1e-6, relative_rmse=1e-6, max_iteration=iters))
+    return result_icp.transformation

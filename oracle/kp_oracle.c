@@ -819,17 +819,163 @@ static void kpo_x6_to_mat4(const double *x, double *M)
     M[8] = -sb;     M[9] = cb * sa;                M[10] = cb * ca;               M[11] = x[5];
     M[12] = 0; M[13] = 0; M[14] = 0; M[15] = 1;
 }
-typedef struct { long n; double err2; } kpo_corr_t;
-KPO_API int kpo_icp_point_to_plane(const float *src, long ns, const float *tgt, const float *tgt_n, long nt,
-                                   double max_corr, const double *init, int max_iter, double rel_fit,
-                                   double rel_rmse, double *T_out, double *fitness_out, double *rmse_out,
-                                   int *iters_out, int64_t *ncorr_out)
+/* ---- Eigen::umeyama without scaling (TransformationEstimationPointToPoint::ComputeTransformation,
+ * manual_pointcloud_registration.py:90-98): R = U diag(1,1,det(U)det(V)) V^T of the cross-covariance
+ * (1/n) sum (t - mt)(s - ms)^T, t = mt - R ms.  SVD by one-sided (Hestenes) Jacobi rotations. */
+static void kpo_svd3(const double C[3][3], double U[3][3], double S[3], double V[3][3])
 {
-    if (!(max_corr > 0) || !tgt_n) return -1;
+    double A[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { A[i][j] = C[i][j]; V[i][j] = i == j; }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0;
+        for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+            double alpha = 0, beta = 0, gamma = 0;
+            for (int k = 0; k < 3; ++k) { alpha += A[k][p] * A[k][p]; beta += A[k][q] * A[k][q]; gamma += A[k][p] * A[k][q]; }
+            if (gamma == 0.0) continue;
+            off = fmax(off, fabs(gamma) / sqrt(alpha * beta + 1e-300));
+            double zeta = (beta - alpha) / (2.0 * gamma);
+            double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+            for (int k = 0; k < 3; ++k) {
+                double ap = A[k][p], aq = A[k][q];
+                A[k][p] = c * ap - sn * aq; A[k][q] = sn * ap + c * aq;
+                double vp = V[k][p], vq = V[k][q];
+                V[k][p] = c * vp - sn * vq; V[k][q] = sn * vp + c * vq;
+            }
+        }
+        if (off < 1e-15) break;
+    }
+    int o[3] = {0, 1, 2};
+    double nrm[3];
+    for (int j = 0; j < 3; ++j) nrm[j] = sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
+    for (int a2 = 0; a2 < 2; ++a2) for (int b2 = a2 + 1; b2 < 3; ++b2) if (nrm[o[b2]] > nrm[o[a2]]) { int t = o[a2]; o[a2] = o[b2]; o[b2] = t; }
+    double Vs[3][3];
+    for (int j = 0; j < 3; ++j) {
+        S[j] = nrm[o[j]];
+        for (int k = 0; k < 3; ++k) { Vs[k][j] = V[k][o[j]]; U[k][j] = S[j] > 1e-300 ? A[k][o[j]] / S[j] : 0.0; }
+    }
+    memcpy(V, Vs, sizeof Vs);
+    /* complete U to an orthonormal basis when singular values vanish */
+    if (!(S[1] > 1e-12 * S[0])) {
+        int ax = fabs(U[0][0]) <= fabs(U[1][0]) && fabs(U[0][0]) <= fabs(U[2][0]) ? 0 : (fabs(U[1][0]) <= fabs(U[2][0]) ? 1 : 2);
+        double e[3] = {0, 0, 0}; e[ax] = 1;
+        double d = U[ax][0], l = 0;
+        for (int k = 0; k < 3; ++k) { U[k][1] = e[k] - d * U[k][0]; l += U[k][1] * U[k][1]; }
+        l = sqrt(l);
+        for (int k = 0; k < 3; ++k) U[k][1] /= l;
+    }
+    if (!(S[2] > 1e-12 * S[0])) {
+        /* third left vector: any unit vector completing the basis; its sign is absorbed by diag(1,1,det U det V) */
+        U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+        U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+        U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+    }
+}
+static double kpo_det3(const double M[3][3])
+{
+    return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+           M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+}
+/* src, tgt: double [n][3] matched rows; out: 4x4 row-major */
+KPO_API void kpo_umeyama(const double *src, const double *tgt, long n, double *T)
+{
+    memset(T, 0, sizeof(double) * 16);
+    T[0] = T[5] = T[10] = T[15] = 1;
+    if (n <= 0) return;
+    double ms[3] = {0, 0, 0}, mt[3] = {0, 0, 0}, C[3][3] = {{0}};
+    for (long i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) { ms[c] += src[3 * i + c]; mt[c] += tgt[3 * i + c]; }
+    for (int c = 0; c < 3; ++c) { ms[c] /= (double)n; mt[c] /= (double)n; }
+    for (long i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) C[a][b] += (tgt[3 * i + a] - mt[a]) * (src[3 * i + b] - ms[b]);
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) C[a][b] /= (double)n;
+    double U[3][3], S[3], V[3][3];
+    kpo_svd3(C, U, S, V);
+    if (!(S[0] > 1e-300)) return;
+    double d = kpo_det3(U) * kpo_det3(V) < 0 ? -1.0 : 1.0;
+    for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) T[4 * a + b] = U[a][0] * V[b][0] + U[a][1] * V[b][1] + d * U[a][2] * V[b][2];
+    }
+    for (int a = 0; a < 3; ++a) T[4 * a + 3] = mt[a] - (T[4 * a] * ms[0] + T[4 * a + 1] * ms[1] + T[4 * a + 2] * ms[2]);
+}
+
+/* ---- InitializePointCloudForColoredICP: tangent-plane colour gradient per point (preprocessing/
+ * registration.py:108-113 via registration_colored_icp); hybrid search (radius, max_nn), >= 4 neighbours. */
+KPO_API int kpo_color_gradient(const float *pts, const float *colors, const float *nrm, long n, double radius, int max_nn,
+                               float *inten_out, float *grad_out)
+{
+    if (!(radius > 0) || max_nn < 1) return -1;
+    for (long i = 0; i < n; ++i)
+        inten_out[i] = (float)((((double)colors[3 * i] + (double)colors[3 * i + 1]) + (double)colors[3 * i + 2]) / 3.0);
+    kpo_grid_t g;
+    kpo_grid_build(&g, pts, n, radius);
+    double r2 = radius * radius;
+#pragma omp parallel
+    {
+        double *bd = (double *)malloc(sizeof(double) * (size_t)max_nn);
+        int32_t *bi = (int32_t *)malloc(sizeof(int32_t) * (size_t)max_nn);
+#pragma omp for schedule(dynamic, 256)
+        for (long i = 0; i < n; ++i) {
+            double x[3] = {0, 0, 0};
+            int cnt = 0;
+            if (!isnan(pts[3 * i])) kpo_query(&g, pts + 3 * i, max_nn, r2, bd, bi, &cnt);
+            if (cnt >= 4) {
+                double vx = pts[3 * i], vy = pts[3 * i + 1], vz = pts[3 * i + 2];
+                double nx = nrm[3 * i], ny = nrm[3 * i + 1], nz = nrm[3 * i + 2], it = inten_out[i];
+                double A[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+                for (int t = 1; t < cnt; ++t) {
+                    long j = bi[t];
+                    double ax = (double)pts[3 * j] - vx, ay = (double)pts[3 * j + 1] - vy, az = (double)pts[3 * j + 2] - vz;
+                    double dn = (ax * nx + ay * ny) + az * nz;
+                    double px = ax - dn * nx, py = ay - dn * ny, pz = az - dn * nz;
+                    double di = (double)inten_out[j] - it;
+                    A[0] += px * px; A[1] += px * py; A[2] += px * pz; A[3] += py * py; A[4] += py * pz; A[5] += pz * pz;
+                    b[0] += px * di; b[1] += py * di; b[2] += pz * di;
+                }
+                double w = (double)(cnt - 1);
+                A[0] += w * nx * w * nx; A[1] += w * nx * w * ny; A[2] += w * nx * w * nz;
+                A[3] += w * ny * w * ny; A[4] += w * ny * w * nz; A[5] += w * nz * w * nz;
+                double M[3][4] = {{A[0], A[1], A[2], b[0]}, {A[1], A[3], A[4], b[1]}, {A[2], A[4], A[5], b[2]}};
+                int ok = 1;
+                for (int c = 0; c < 3 && ok; ++c) {
+                    int pv = c;
+                    for (int r = c + 1; r < 3; ++r) if (fabs(M[r][c]) > fabs(M[pv][c])) pv = r;
+                    if (!(fabs(M[pv][c]) > 1e-300)) { ok = 0; break; }
+                    if (pv != c) for (int j = 0; j < 4; ++j) { double tv = M[c][j]; M[c][j] = M[pv][j]; M[pv][j] = tv; }
+                    for (int r = c + 1; r < 3; ++r) { double f = M[r][c] / M[c][c]; for (int j = c; j < 4; ++j) M[r][j] -= f * M[c][j]; }
+                }
+                if (ok) {
+                    x[2] = M[2][3] / M[2][2];
+                    x[1] = (M[1][3] - M[1][2] * x[2]) / M[1][1];
+                    x[0] = (M[0][3] - M[0][1] * x[1] - M[0][2] * x[2]) / M[0][0];
+                    if (!(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]))) x[0] = x[1] = x[2] = 0;
+                }
+            }
+            grad_out[3 * i] = (float)x[0]; grad_out[3 * i + 1] = (float)x[1]; grad_out[3 * i + 2] = (float)x[2];
+        }
+        free(bd); free(bi);
+    }
+    kpo_grid_free(&g);
+    return 0;
+}
+
+/* ---- the ICP loop of registration_icp for the three estimators the reference uses:
+ * mode 0 point-to-plane (preprocessing/registration.py:78-84), 1 point-to-point
+ * (manual_pointcloud_registration.py:94-98), 2 coloured (preprocessing/registration.py:108-113;
+ * src_int / tgt_int / tgt_grad from kpo_color_gradient, lambda = lambda_geometric). */
+KPO_API int kpo_icp(int mode, const float *src, long ns, const float *tgt, const float *tgt_n, long nt,
+                    const float *src_int, const float *tgt_int, const float *tgt_grad, double lambda,
+                    double max_corr, const double *init, int max_iter, double rel_fit,
+                    double rel_rmse, double *T_out, double *fitness_out, double *rmse_out,
+                    int *iters_out, int64_t *ncorr_out)
+{
+    if (!(max_corr > 0) || (mode != 1 && !tgt_n)) return -1;
     kpo_grid_t g;
     kpo_grid_build(&g, tgt, nt, max_corr);
     double r2 = max_corr * max_corr;
+    double slg = sqrt(lambda), slp = sqrt(1.0 - lambda);
     double *cur = (double *)malloc(sizeof(double) * 3 * (size_t)(ns ? ns : 1));
+    double *ms = (double *)malloc(sizeof(double) * 3 * (size_t)(ns ? ns : 1));
+    double *mt = (double *)malloc(sizeof(double) * 3 * (size_t)(ns ? ns : 1));
     int32_t *corr = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ns ? ns : 1));
     double T[16];
     memcpy(T, init, sizeof T);
@@ -873,10 +1019,29 @@ KPO_API int kpo_icp_point_to_plane(const float *src, long ns, const float *tgt, 
             double sx = cur[3 * i], sy = cur[3 * i + 1], sz = cur[3 * i + 2];
             double ex = sx - (double)tgt[3 * j], ey = sy - (double)tgt[3 * j + 1], ez = sz - (double)tgt[3 * j + 2];
             err2 += (ex * ex + ey * ey) + ez * ez;
+            if (mode == 1) {
+                ms[3 * nc] = sx; ms[3 * nc + 1] = sy; ms[3 * nc + 2] = sz;
+                mt[3 * nc] = tgt[3 * j]; mt[3 * nc + 1] = tgt[3 * j + 1]; mt[3 * nc + 2] = tgt[3 * j + 2];
+                ++nc;
+                continue;
+            }
             ++nc;
             double nx = tgt_n[3 * j], ny = tgt_n[3 * j + 1], nz = tgt_n[3 * j + 2];
             double r = (ex * nx + ey * ny) + ez * nz;
             double J[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
+            if (mode == 2) {
+                double is = src_int[i], it = tgt_int[j];
+                double gx = tgt_grad[3 * j], gy = tgt_grad[3 * j + 1], gz = tgt_grad[3 * j + 2];
+                double px = ex - r * nx, py = ey - r * ny, pz = ez - r * nz;       /* vs_proj - vt */
+                double is_proj = ((gx * px + gy * py) + gz * pz) + it;
+                double gn = (gx * nx + gy * ny) + gz * nz;
+                double mx = -(gx - gn * nx), my = -(gy - gn * ny), mz = -(gz - gn * nz);   /* -dit^T (I - n n^T) */
+                double J2[6] = {slp * (sy * mz - sz * my), slp * (sz * mx - sx * mz), slp * (sx * my - sy * mx), slp * mx, slp * my, slp * mz};
+                double r2c = slp * (is - is_proj);
+                for (int p = 0; p < 6; ++p) J[p] *= slg;
+                r *= slg;
+                for (int p = 0; p < 6; ++p) { b[p] += J2[p] * r2c; for (int q = 0; q < 6; ++q) A[p][q] += J2[p] * J2[q]; }
+            }
             for (int p = 0; p < 6; ++p) { b[p] += J[p] * r; for (int q = 0; q < 6; ++q) A[p][q] += J[p] * J[q]; }
         }
         pfit = fit; prmse = rmse;
@@ -888,9 +1053,13 @@ KPO_API int kpo_icp_point_to_plane(const float *src, long ns, const float *tgt, 
         }
         if (pass == max_iter) break;
         double x[6], U[16];
-        for (int p = 0; p < 6; ++p) b[p] = -b[p];
-        if (nc > 0 && kpo_solve6(A, b, x)) kpo_x6_to_mat4(x, U);
-        else { memset(U, 0, sizeof U); U[0] = U[5] = U[10] = U[15] = 1; }
+        memset(U, 0, sizeof U); U[0] = U[5] = U[10] = U[15] = 1;
+        if (mode == 1) {
+            if (nc > 0) kpo_umeyama(ms, mt, nc, U);
+        } else {
+            for (int p = 0; p < 6; ++p) b[p] = -b[p];
+            if (nc > 0 && kpo_solve6(A, b, x)) kpo_x6_to_mat4(x, U);
+        }
         kpo_mat4_mul(U, T, T);
         for (long i = 0; i < ns; ++i) {
             double X = cur[3 * i], Y = cur[3 * i + 1], Z = cur[3 * i + 2];
@@ -904,9 +1073,17 @@ KPO_API int kpo_icp_point_to_plane(const float *src, long ns, const float *tgt, 
     if (rmse_out) *rmse_out = rmse;
     if (iters_out) *iters_out = it_done;
     if (ncorr_out) *ncorr_out = nc;
-    free(cur); free(corr);
+    free(cur); free(corr); free(ms); free(mt);
     kpo_grid_free(&g);
     return 0;
+}
+KPO_API int kpo_icp_point_to_plane(const float *src, long ns, const float *tgt, const float *tgt_n, long nt,
+                                   double max_corr, const double *init, int max_iter, double rel_fit,
+                                   double rel_rmse, double *T_out, double *fitness_out, double *rmse_out,
+                                   int *iters_out, int64_t *ncorr_out)
+{
+    return kpo_icp(0, src, ns, tgt, tgt_n, nt, NULL, NULL, NULL, 1.0, max_corr, init, max_iter, rel_fit, rel_rmse, T_out,
+                   fitness_out, rmse_out, iters_out, ncorr_out);
 }
 
 KPO_API int kpo_num_threads(void)

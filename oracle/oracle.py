@@ -72,6 +72,41 @@ def rng(seed, a, b) -> int:
     return int(lib().kpo_rng(C.c_uint64(seed), C.c_uint64(a), C.c_uint64(b)))
 
 
+def _mix64_np(z):
+    z = (z + np.uint64(0x9E3779B97F4A7C15))
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def rng_array(seed, a, b):
+    """kp_rng(seed, a, b[i]) for an index array b (vectorised restatement of kpo_rng)."""
+    with np.errstate(over="ignore"):
+        s = _mix64_np(np.uint64(seed & 0xFFFFFFFFFFFFFFFF))
+        s = _mix64_np(s + np.uint64(a & 0xFFFFFFFFFFFFFFFF))
+        return _mix64_np(s + np.asarray(b, dtype=np.uint64))
+
+
+def resample_fixed_n(pts, N, mode="random", seed=1234, stream=0):
+    """Fixed-N resampling (select_points_randomly, utils/processing.py:259-275; points[:N],
+    datasets/kinect_dataset_npz.py:97).  Random mode: the N valid points with the smallest
+    (key, index), key = min(rng(seed, stream, i) >> 32, 2^32 - 2), NaN rows excluded; ValueError when
+    fewer than N valid points exist (np.random.choice(replace=False) raises it).  Returns (points, indices)."""
+    pts = _f32(pts).reshape(-1, 3)
+    n = pts.shape[0]
+    if mode == "prefix":
+        m = min(n, int(N))
+        return pts[:m].copy(), np.arange(m, dtype=np.int32)
+    key = (rng_array(seed, stream, np.arange(n, dtype=np.uint64)) >> np.uint64(32)).astype(np.uint64)
+    key = np.minimum(key, np.uint64(0xFFFFFFFE))
+    valid = ~np.isnan(pts[:, 0])
+    key[~valid] = np.uint64(0xFFFFFFFF)
+    if int(N) > int(valid.sum()):
+        raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+    order = np.argsort(key, kind="stable")[:int(N)].astype(np.int32)
+    return pts[order].copy(), order
+
+
 def csum(x) -> float:
     x = np.ascontiguousarray(x, dtype=np.float64)
     return float(lib().kpo_csum(_p(x), C.c_long(x.size)))
@@ -241,6 +276,55 @@ def icp_point_to_plane(src, tgt, tgt_normals, max_corr, init=None, max_iter=30, 
     if rc != 0:
         raise ValueError("oracle icp: bad arguments")
     return {"T": T.reshape(4, 4), "fitness": fit.value, "rmse": rmse.value, "iters": iters.value, "ncorr": nc.value}
+
+
+def umeyama(src, tgt):
+    """TransformationEstimationPointToPoint.compute_transformation on matched rows (manual_pointcloud_registration.py:90-92)."""
+    a = np.ascontiguousarray(src, dtype=np.float64).reshape(-1, 3)
+    b = np.ascontiguousarray(tgt, dtype=np.float64).reshape(-1, 3)
+    T = np.zeros(16, np.float64)
+    lib().kpo_umeyama(_p(a), _p(b), C.c_long(a.shape[0]), _p(T))
+    return T.reshape(4, 4)
+
+
+def color_gradient(pts, colors, normals, radius, max_nn=30):
+    """(intensity, gradient) of InitializePointCloudForColoredICP (under registration_colored_icp, registration.py:108)."""
+    pts, col, nrm = _f32(pts), _f32(colors), _f32(normals)
+    n = pts.shape[0]
+    inten = np.zeros((n,), np.float32)
+    grad = np.zeros((n, 3), np.float32)
+    if lib().kpo_color_gradient(_p(pts), _p(col), _p(nrm), C.c_long(n), C.c_double(radius), C.c_int(max_nn), _p(inten), _p(grad)) != 0:
+        raise ValueError("oracle color_gradient: bad arguments")
+    return inten, grad
+
+
+def _icp(mode, src, tgt, tgt_normals, src_int, tgt_int, tgt_grad, lam, max_corr, init, max_iter, rel_fit, rel_rmse):
+    src, tgt = _f32(src), _f32(tgt)
+    tn = None if tgt_normals is None else _f32(tgt_normals)
+    T0 = np.ascontiguousarray(np.eye(4) if init is None else init, dtype=np.float64).reshape(16)
+    T = np.zeros(16, np.float64)
+    fit, rmse, iters, nc = C.c_double(), C.c_double(), C.c_int(), C.c_int64()
+    rc = lib().kpo_icp(C.c_int(mode), _p(src), C.c_long(src.shape[0]), _p(tgt), _p(tn), C.c_long(tgt.shape[0]),
+                       _p(src_int), _p(tgt_int), _p(tgt_grad), C.c_double(lam), C.c_double(max_corr), _p(T0), C.c_int(max_iter),
+                       C.c_double(rel_fit), C.c_double(rel_rmse), _p(T), C.byref(fit), C.byref(rmse), C.byref(iters), C.byref(nc))
+    if rc != 0:
+        raise ValueError("oracle icp: bad arguments")
+    return {"T": T.reshape(4, 4), "fitness": fit.value, "rmse": rmse.value, "iters": iters.value, "ncorr": nc.value}
+
+
+def icp_point_to_point(src, tgt, max_corr, init=None, max_iter=30, rel_fit=1e-6, rel_rmse=1e-6):
+    """registration_icp(..., TransformationEstimationPointToPoint()) (manual_pointcloud_registration.py:94-98)."""
+    return _icp(1, src, tgt, None, None, None, None, 1.0, max_corr, init, max_iter, rel_fit, rel_rmse)
+
+
+def icp_colored(src, src_colors, tgt, tgt_colors, tgt_normals, max_corr, init=None, max_iter=30, rel_fit=1e-6,
+                rel_rmse=1e-6, lambda_geometric=0.968):
+    """registration_colored_icp (preprocessing/registration.py:108-113)."""
+    sc = _f32(src_colors)
+    s_int = ((sc[:, 0].astype(np.float64) + sc[:, 1].astype(np.float64)) + sc[:, 2].astype(np.float64)) / 3.0
+    s_int = s_int.astype(np.float32)
+    t_int, t_grad = color_gradient(tgt, tgt_colors, tgt_normals, 2.0 * max_corr, 30)
+    return _icp(2, src, tgt, tgt_normals, s_int, t_int, t_grad, lambda_geometric, max_corr, init, max_iter, rel_fit, rel_rmse)
 
 
 # ------------------------------------------------------------ compositions --

@@ -183,3 +183,55 @@ def icp(ctx, src, tgt, tgt_n, max_corr, init=None, max_iter=30, rel_fit=1e-6, re
                                             T0.ctypes.data, max_iter, rel_fit, rel_rmse, T.ctypes.data, C.byref(fit),
                                             C.byref(rmse), C.byref(iters), C.byref(nc)))
     return {"T": T.reshape(4, 4), "fitness": fit.value, "rmse": rmse.value, "iters": iters.value, "ncorr": nc.value}
+
+
+def resample(ctx, xyz, N, mode=0, seed=1234, stream=0):
+    d = ctx.to_device(xyz, np.float32)
+    n = d.shape[0]
+    out = ctx.empty((max(N, 1), 3), np.float32)
+    idx = ctx.empty((max(N, 1),), np.int32)
+    cnt = C.c_int64()
+    ctx.check(ctx.lib.kp_resample_fixed_n(ctx.handle, d.ptr, n, N, mode, seed, stream, out.ptr, idx.ptr, C.byref(cnt)))
+    m = cnt.value
+    return out.to_host(m), idx.to_host(m)
+
+
+def resample_batch(ctx, clouds, N, mode=0, seed=1234, first_stream=0):
+    off = np.zeros(len(clouds) + 1, np.int64)
+    off[1:] = np.cumsum([c.shape[0] for c in clouds])
+    flat = ctx.to_device(np.concatenate(clouds, axis=0), np.float32)
+    out = ctx.empty((len(clouds), N, 3), np.float32)
+    counts = np.zeros(len(clouds), np.int64)
+    ctx.check(ctx.lib.kp_resample_batch(ctx.handle, flat.ptr, off.ctypes.data_as(C.POINTER(C.c_int64)), len(clouds), N, mode,
+                                        seed, first_stream, out.ptr, counts.ctypes.data_as(C.POINTER(C.c_int64))))
+    return out.to_host(), counts
+
+
+def icp_p2p(ctx, src, tgt, max_corr, init=None, max_iter=30, rel_fit=1e-6, rel_rmse=1e-6):
+    ds, dt = ctx.to_device(src, np.float32), ctx.to_device(tgt, np.float32)
+    T0 = _cabi.T16(np.eye(4) if init is None else init)
+    T = np.zeros(16)
+    fit, rmse, iters, nc = C.c_double(), C.c_double(), C.c_int(), C.c_int64()
+    ctx.check(ctx.lib.kp_icp_point_to_point(ctx.handle, ds.ptr, ds.shape[0], dt.ptr, dt.shape[0], float(max_corr),
+                                            T0.ctypes.data, max_iter, rel_fit, rel_rmse, T.ctypes.data, C.byref(fit),
+                                            C.byref(rmse), C.byref(iters), C.byref(nc)))
+    return {"T": T.reshape(4, 4), "fitness": fit.value, "rmse": rmse.value, "iters": iters.value, "ncorr": nc.value}
+
+
+def icp_colored(ctx, src, src_col, tgt, tgt_col, tgt_n, max_corr, init=None, max_iter=30, rel_fit=1e-6, rel_rmse=1e-6, lam=0.968):
+    ds, dsc = ctx.to_device(src, np.float32), ctx.to_device(src_col, np.float32)
+    dt, dtc, dn = ctx.to_device(tgt, np.float32), ctx.to_device(tgt_col, np.float32), ctx.to_device(tgt_n, np.float32)
+    T0 = _cabi.T16(np.eye(4) if init is None else init)
+    T = np.zeros(16)
+    fit, rmse, iters, nc = C.c_double(), C.c_double(), C.c_int(), C.c_int64()
+    ctx.check(ctx.lib.kp_icp_colored(ctx.handle, ds.ptr, dsc.ptr, ds.shape[0], dt.ptr, dtc.ptr, dn.ptr, dt.shape[0],
+                                     float(max_corr), float(lam), T0.ctypes.data, max_iter, rel_fit, rel_rmse, T.ctypes.data,
+                                     C.byref(fit), C.byref(rmse), C.byref(iters), C.byref(nc)))
+    return {"T": T.reshape(4, 4), "fitness": fit.value, "rmse": rmse.value, "iters": iters.value, "ncorr": nc.value}
+
+
+def color_gradient(ctx, xyz, colors, normals, radius, max_nn=30):
+    d, dc, dn = ctx.to_device(xyz, np.float32), ctx.to_device(colors, np.float32), ctx.to_device(normals, np.float32)
+    out = ctx.empty(d.shape, np.float32)
+    ctx.check(ctx.lib.kp_color_gradient(ctx.handle, d.ptr, dc.ptr, dn.ptr, d.shape[0], float(radius), max_nn, out.ptr))
+    return out.to_host()

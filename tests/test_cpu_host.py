@@ -100,7 +100,7 @@ def test_reference_surface_signatures():
     assert sig(registration.prepare_dataset) == [("pcd_master", E), ("pcd_sub", E), ("voxel_size", E), ("normals_nn", 40), ("fpfh_nn", 40)]
     assert sig(registration.execute_global_registration) == [("pcd_master", E), ("pcd_sub", E), ("voxel_size", 35), ("ransac_n_trials", 15)]
     assert sig(registration.execute_point_to_plane_registration)[:4] == [("pcd_master", E), ("pcd_sub", E), ("initial_transformation", E), ("voxel_size", 35)]
-    assert sig(registration.execute_colored_ICP_registration) == [("pcd_master", E), ("pcd_sub", E), ("initial_transformation", E)]
+    assert sig(registration.execute_colored_ICP_registration)[:3] == [("pcd_master", E), ("pcd_sub", E), ("initial_transformation", E)]
     assert sig(floor_removal.equation_plane) == [("p1", E), ("p2", E), ("p3", E)]
     assert sig(floor_removal.pcd_above_plane) == [("a", E), ("b", E), ("c", E), ("d", E), ("pcd", E)]
     assert sig(kio.rgbd_to_pointcloud)[:2] == [("color_img", E), ("depth_img", E)]
