@@ -238,6 +238,34 @@ KP_EXPORT int kp_icp_colored(kp_ctx *ctx, const float *d_src, const float *d_src
 KP_EXPORT int kp_color_gradient(kp_ctx *ctx, const float *d_xyz, const float *d_colors, const float *d_normals,
                                 int64_t n, double radius, int max_nn, float *d_grad);
 
+/* ---------------------------------------------- global registration ----- */
+/* compute_fpfh_feature(pcd, KDTreeSearchParamHybrid(radius, max_nn)) at
+ * preprocessing/registration.py:17-20: 33-bin FPFH per point (SPFH of the Darboux angles over the hybrid
+ * neighbourhood, then the 1/d^2-weighted blend of the neighbours' SPFHs plus the point's own).
+ * d_feat float64 [n][33] (Open3D stores the transpose, 33 x n). */
+KP_EXPORT int kp_fpfh(kp_ctx *ctx, const float *d_xyz, const float *d_normals, int64_t n, double radius,
+                      int max_nn, double *d_feat);
+/* Exact nearest neighbour of every feature a_i among the features b (squared L2 in double, summed in
+ * dimension order; ties to the lower index): the two KD-tree searches inside
+ * registration_ransac_based_on_feature_matching (preprocessing/registration.py:50).  dim must be 33.
+ * d_nn int32 [na]; d_nn_d2 float64 [na] nullable. */
+KP_EXPORT int kp_feature_match(kp_ctx *ctx, const double *d_feat_a, int64_t na, const double *d_feat_b,
+                               int64_t nb, int dim, int32_t *d_nn, double *d_nn_d2);
+/* RegistrationRANSACBasedOnCorrespondence, the second half of
+ * registration_ransac_based_on_feature_matching (preprocessing/registration.py:50-57) with
+ * TransformationEstimationPointToPoint(False), CorrespondenceCheckerBasedOnEdgeLength(edge_similarity),
+ * CorrespondenceCheckerBasedOnDistance(distance_threshold) and RANSACConvergenceCriteria(max_iteration,
+ * confidence).  Hypothesis h samples correspondence kp_rng(seed, h, j) % m for j < ransac_n (with
+ * replacement).  d_corres int32 [m][2] = (source index, target index).  h_T16 row-major 4x4 (identity
+ * when nothing validates); h_best_iter = hypothesis that won (-1 if none); h_validated = hypotheses that
+ * passed the checkers. */
+KP_EXPORT int kp_ransac_correspondence(kp_ctx *ctx, const float *d_src, int64_t n_src, const float *d_tgt,
+                                       int64_t n_tgt, const int32_t *d_corres, int64_t m, double max_corr,
+                                       int ransac_n, double edge_similarity, double distance_threshold,
+                                       int max_iteration, double confidence, uint64_t seed, double *h_T16,
+                                       double *h_fitness, double *h_rmse, int32_t *h_best_iter,
+                                       int64_t *h_validated);
+
 /* ----------------------------------------------------- K6 resample ----- */
 /* Fixed-N resampling feeding PointNet (BASELINE config C5).
  *   KP_RESAMPLE_RANDOM: select_points_randomly (utils/processing.py:259-275,

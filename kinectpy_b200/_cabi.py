@@ -100,6 +100,10 @@ SIGNATURES = {
     "kp_icp_colored": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _f64, _f64, _vp, C.c_int, _f64, _f64, _vp, _pf64, _pf64,
                                  C.POINTER(C.c_int), _pi64]),
     "kp_color_gradient": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f64, C.c_int, _vp]),
+    "kp_fpfh": (C.c_int, [_vp, _vp, _vp, _i64, _f64, C.c_int, _vp]),
+    "kp_feature_match": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),
+    "kp_ransac_correspondence": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _f64, C.c_int, _f64, _f64, C.c_int, _f64, _u64,
+                                           _pf64, _pf64, _pf64, _pi32, _pi64]),
     "kp_resample_fixed_n": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _u64, _u64, _vp, _vp, _pi64]),
     "kp_resample_batch": (C.c_int, [_vp, _vp, _pi64, C.c_int, _i64, C.c_int, _u64, _u64, _vp, _pi64]),
     "kp_pipeline_create": (C.c_int, [C.c_int, C.POINTER(PipelineCfg), _vp, _vp, C.POINTER(_vp)]),

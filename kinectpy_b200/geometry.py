@@ -433,7 +433,8 @@ class ICPConvergenceCriteria:
 
 
 class RegistrationResult:
-    def __init__(self, T, fitness, rmse, iters, ncorr):
+    def __init__(self, T, fitness, rmse, iters, ncorr, correspondence_set=None):
+        self.correspondence_set = correspondence_set
         self.transformation = T
         self.fitness = fitness
         self.inlier_rmse = rmse
@@ -505,3 +506,126 @@ def registration_colored_icp(source: PointCloud, target: PointCloud, max_corresp
                                      int(crit.max_iteration), float(crit.relative_fitness), float(crit.relative_rmse),
                                      T.ctypes.data, C.byref(fit), C.byref(rmse), C.byref(iters), C.byref(nc)))
     return RegistrationResult(T.reshape(4, 4).copy(), fit.value, rmse.value, iters.value, nc.value)
+
+
+# ----------------------------------------------------- global registration --
+class Feature:
+    """``o3d.pipelines.registration.Feature``: ``data`` is ``float64 (dimension, num)`` like Open3D's; the
+    device copy (``float64 [num][dimension]``) is kept for the matching kernels."""
+
+    def __init__(self, ctx=None, dev: Optional[DeviceArray] = None, num: int = 0, dim: int = 33):
+        self._ctx, self._devarr, self._num, self._dim, self._host = ctx, dev, int(num), int(dim), None
+
+    def dimension(self) -> int:
+        return self._dim
+
+    def num(self) -> int:
+        return self._num
+
+    @property
+    def data(self) -> np.ndarray:
+        if self._host is None:
+            self._host = (self._devarr.to_host(self._num).T.copy() if self._devarr is not None
+                          else np.zeros((self._dim, 0), np.float64))
+        return self._host
+
+    def _device(self, ctx) -> DeviceArray:
+        if self._devarr is None:
+            self._devarr = ctx.to_device(np.ascontiguousarray(self.data.T), np.float64)
+        return self._devarr
+
+
+def compute_fpfh_feature(input: PointCloud, search_param) -> Feature:
+    """``o3d.pipelines.registration.compute_fpfh_feature`` (``registration.py:17-20``)."""
+    if not input.has_normals():
+        raise KinectPyB200Error(_cabi.KP_E_ARG, "compute_fpfh_feature: the cloud has no normals")
+    radius = float(getattr(search_param, "radius", 0.0) or 0.0)
+    max_nn = int(getattr(search_param, "max_nn", getattr(search_param, "knn", 100)))
+    ctx, pts, _, nrm = input._dev()
+    n = len(input)
+    feat = ctx.empty((max(n, 1), 33), np.float64)
+    ctx.check(ctx.lib.kp_fpfh(ctx.handle, PointCloud._ptr(pts), PointCloud._ptr(nrm), n, radius, max_nn, feat.ptr))
+    return Feature(ctx, feat, n, 33)
+
+
+class CorrespondenceCheckerBasedOnEdgeLength:
+    def __init__(self, similarity_threshold: float = 0.9):
+        self.similarity_threshold = float(similarity_threshold)
+
+
+class CorrespondenceCheckerBasedOnDistance:
+    def __init__(self, distance_threshold: float):
+        self.distance_threshold = float(distance_threshold)
+
+
+class CorrespondenceCheckerBasedOnNormal:
+    def __init__(self, normal_angle_threshold: float):
+        raise NotImplementedError("CorrespondenceCheckerBasedOnNormal is not used by the reference")
+
+
+class RANSACConvergenceCriteria:
+    def __init__(self, max_iteration: int = 100000, confidence: float = 0.999):
+        self.max_iteration, self.confidence = int(max_iteration), float(confidence)
+
+
+_RANSAC_CALLS = [0]   # successive calls draw different hypothesis streams, as successive upstream calls advance the global RNG
+
+
+def registration_ransac_based_on_feature_matching(source: PointCloud, target: PointCloud, source_feature: Feature,
+                                                  target_feature: Feature, mutual_filter: bool,
+                                                  max_correspondence_distance: float, estimation_method=None,
+                                                  ransac_n: int = 3, checkers=(), criteria=None, seed: Optional[int] = None
+                                                  ) -> RegistrationResult:
+    """``o3d.pipelines.registration.registration_ransac_based_on_feature_matching`` (``registration.py:50-57``):
+    nearest feature of every source point among the target's (and back, for the mutual filter), then RANSAC
+    over those correspondences.  Matching, hypothesis checking and scoring run on the GPU; the mutual filter is
+    an index comparison on the host."""
+    if estimation_method is not None and not isinstance(estimation_method, TransformationEstimationPointToPoint):
+        raise NotImplementedError("only TransformationEstimationPointToPoint(False) is used by the reference")
+    crit = criteria or RANSACConvergenceCriteria()
+    if ransac_n < 3 or not max_correspondence_distance > 0:
+        return RegistrationResult(np.eye(4), 0.0, 0.0, 0, 0, np.zeros((0, 2), np.int32))
+    edge, dist = 0.0, 0.0
+    for ch in checkers:
+        if isinstance(ch, CorrespondenceCheckerBasedOnEdgeLength):
+            edge = ch.similarity_threshold
+        elif isinstance(ch, CorrespondenceCheckerBasedOnDistance):
+            dist = ch.distance_threshold
+        else:
+            raise NotImplementedError("unsupported correspondence checker %r" % (ch,))
+    ctx, s_pts, _, _ = source._dev()
+    _, t_pts, _, _ = target._dev()
+    ns, nt = len(source), len(target)
+    fs, ft = source_feature._device(ctx), target_feature._device(ctx)
+    nn_st = ctx.empty((max(ns, 1),), np.int32)
+    ctx.check(ctx.lib.kp_feature_match(ctx.handle, fs.ptr, ns, ft.ptr, nt, 33, nn_st.ptr, None))
+    st = nn_st.to_host(ns)
+    corres = np.stack([np.arange(ns, dtype=np.int32), st], axis=1)
+    if mutual_filter:
+        nn_ts = ctx.empty((max(nt, 1),), np.int32)
+        ctx.check(ctx.lib.kp_feature_match(ctx.handle, ft.ptr, nt, fs.ptr, ns, 33, nn_ts.ptr, None))
+        ts = nn_ts.to_host(nt)
+        mut = corres[ts[st] == np.arange(ns)] if ns and nt else corres[:0]
+        if len(mut) >= ransac_n * 3:
+            corres = mut                                   # else: too few, fall back to the unfiltered set (upstream)
+    corres = np.ascontiguousarray(corres, dtype=np.int32)
+    if seed is None:
+        seed = (_SEED[0] + 0x9E3779B97F4A7C15 * _RANSAC_CALLS[0]) & 0xFFFFFFFFFFFFFFFF
+        _RANSAC_CALLS[0] += 1
+    d_cor = ctx.to_device(corres, np.int32)
+    T = np.zeros(16, np.float64)
+    fit, rmse, best, val = C.c_double(), C.c_double(), C.c_int32(), C.c_int64()
+    ctx.check(ctx.lib.kp_ransac_correspondence(ctx.handle, PointCloud._ptr(s_pts), ns, PointCloud._ptr(t_pts), nt, d_cor.ptr,
+                                               len(corres), float(max_correspondence_distance), int(ransac_n), edge, dist,
+                                               crit.max_iteration, crit.confidence, int(seed), T.ctypes.data_as(C.POINTER(C.c_double)),
+                                               C.byref(fit), C.byref(rmse), C.byref(best), C.byref(val)))
+    T = T.reshape(4, 4).copy()
+    # correspondence_set of the result: the correspondences the winning transform brings within the threshold
+    inl = corres[:0]
+    if fit.value > 0 and len(corres):
+        sp = np.asarray(source.points)[corres[:, 0]] @ T[:3, :3].T + T[:3, 3]
+        d2 = ((sp - np.asarray(target.points)[corres[:, 1]]) ** 2).sum(axis=1)
+        inl = corres[d2 < max_correspondence_distance ** 2]
+    res = RegistrationResult(T, fit.value, rmse.value, int(best.value), len(inl), inl)
+    res.num_validated = int(val.value)
+    return res

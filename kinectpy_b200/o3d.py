@@ -26,8 +26,12 @@ pipelines = SimpleNamespace(registration=SimpleNamespace(
     TransformationEstimationPointToPoint=_g.TransformationEstimationPointToPoint,
     ICPConvergenceCriteria=_g.ICPConvergenceCriteria,
     RegistrationResult=_g.RegistrationResult,
-    compute_fpfh_feature=_not_on_path("compute_fpfh_feature"),
-    registration_ransac_based_on_feature_matching=_not_on_path("registration_ransac_based_on_feature_matching"),
+    compute_fpfh_feature=_g.compute_fpfh_feature,
+    registration_ransac_based_on_feature_matching=_g.registration_ransac_based_on_feature_matching,
+    Feature=_g.Feature,
+    CorrespondenceCheckerBasedOnEdgeLength=_g.CorrespondenceCheckerBasedOnEdgeLength,
+    CorrespondenceCheckerBasedOnDistance=_g.CorrespondenceCheckerBasedOnDistance,
+    RANSACConvergenceCriteria=_g.RANSACConvergenceCriteria,
     registration_colored_icp=_g.registration_colored_icp,
     TransformationEstimationForColoredICP=_g.TransformationEstimationForColoredICP,
 ))

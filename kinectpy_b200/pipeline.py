@@ -146,10 +146,11 @@ class FramePipeline:
         self._last_raw = res
         return outs
 
-    def run_raw(self, depth_ptr: int, on_device: bool, n_frames: int):
-        """Timing form: no numpy conversion of the results (returns the ctypes result array)."""
+    def run_raw(self, depth_ptr: int, on_device: bool, n_frames: int, d_out_ptr=None, out_stride: int = 0):
+        """Timing form: no numpy conversion of the results (returns the ctypes result array).  ``d_out_ptr``:
+        optional device buffer ``float32 [n_frames][out_stride][3]`` receiving each frame's final cloud."""
         res = (FrameResult * n_frames)()
-        rc = self.lib.kp_pipeline_run(self.handle, depth_ptr, 1 if on_device else 0, n_frames, res, None, 0)
+        rc = self.lib.kp_pipeline_run(self.handle, depth_ptr, 1 if on_device else 0, n_frames, res, d_out_ptr, out_stride)
         if rc != 0:
             self._raise(rc)
         return res

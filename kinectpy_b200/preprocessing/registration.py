@@ -21,12 +21,14 @@ from ..geometry import PointCloud
 def preprocess_point_cloud(pcd: PointCloud, voxel_size, normals_nn=30, fpfh_nn=100):
     """voxel -> normals (hybrid search: radius 2*voxel, at most ``normals_nn``) (``registration.py:7-21``).
 
-    The second return value is the FPFH feature in the reference; it is computed lazily there too
-    (the ICP wrapper throws it away, ``registration.py:77``) and is ``None`` here.
-    """
+    then FPFH over the hybrid neighbourhood of radius 5*voxel, at most ``fpfh_nn``.  ``fpfh_nn=None`` skips
+    the feature (the ICP wrapper throws it away, ``registration.py:77``)."""
     down = pcd.voxel_down_sample(voxel_size)
     down.estimate_normals(_g.KDTreeSearchParamHybrid(radius=voxel_size * 2, max_nn=normals_nn))
-    return down, None
+    if fpfh_nn is None:
+        return down, None
+    fpfh = _g.compute_fpfh_feature(down, _g.KDTreeSearchParamHybrid(radius=voxel_size * 5, max_nn=fpfh_nn))
+    return down, fpfh
 
 
 def prepare_dataset(pcd_master, pcd_sub, voxel_size, normals_nn=40, fpfh_nn=40):
@@ -37,9 +39,24 @@ def prepare_dataset(pcd_master, pcd_sub, voxel_size, normals_nn=40, fpfh_nn=40):
 
 
 def execute_global_registration(pcd_master, pcd_sub, voxel_size: int = 35, ransac_n_trials: int = 15) -> np.ndarray:
-    raise NotImplementedError("FPFH + feature-matching RANSAC global registration is a 'next' row "
-                              "(SURVEY.md section 8f, f3); pass an initial transformation to "
-                              "execute_point_to_plane_registration instead")
+    """FPFH + feature-matching RANSAC (``registration.py:32-62``): ``ransac_n_trials`` independent RANSAC runs
+    (250 000 hypotheses, confidence 0.999, edge-length 0.95 and distance checkers, mutual filter), the
+    transformation of the fittest one is returned; it maps ``pcd_sub`` into the frame of ``pcd_master``.
+    ``prepare_dataset`` is deterministic, so it is evaluated once instead of once per trial."""
+    best_fitness = 0
+    ransac_transformation = None
+    (source, target, source_down, target_down, source_fpfh, target_fpfh) = prepare_dataset(pcd_master, pcd_sub, voxel_size)
+    distance_threshold = voxel_size * 1.5
+    for _ in range(ransac_n_trials):
+        result_ransac = _g.registration_ransac_based_on_feature_matching(
+            source_down, target_down, source_fpfh, target_fpfh, True, distance_threshold,
+            _g.TransformationEstimationPointToPoint(False), 3,
+            [_g.CorrespondenceCheckerBasedOnEdgeLength(0.95), _g.CorrespondenceCheckerBasedOnDistance(distance_threshold)],
+            _g.RANSACConvergenceCriteria(250000, 0.999))
+        if best_fitness < result_ransac.fitness:
+            best_fitness = result_ransac.fitness
+            ransac_transformation = result_ransac.transformation
+    return ransac_transformation
 
 
 def execute_point_to_plane_registration(pcd_master, pcd_sub, initial_transformation, voxel_size: int = 35,
@@ -51,8 +68,9 @@ def execute_point_to_plane_registration(pcd_master, pcd_sub, initial_transformat
     30 iterations, 1e-6 / 1e-6.
     """
     first, second = copy.deepcopy(pcd_master), copy.deepcopy(pcd_sub)
-    # the reference passes (master, sub) into prepare_dataset(pcd_master, pcd_sub): source <- sub, target <- master
-    _, _, source_down, target_down, _, _ = prepare_dataset(first, second, voxel_size)
+    # the reference passes (master, sub) into prepare_dataset(pcd_master, pcd_sub): source <- sub, target <- master.
+    # Its FPFH features are computed and dropped there (registration.py:77); fpfh_nn=None skips them.
+    _, _, source_down, target_down, _, _ = prepare_dataset(first, second, voxel_size, fpfh_nn=None)
     result = _g.registration_icp(source_down, target_down, threshold, initial_transformation,
                                  _g.TransformationEstimationPointToPlane())
     return result if return_result else result.transformation

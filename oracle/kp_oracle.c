@@ -1086,6 +1086,171 @@ KPO_API int kpo_icp_point_to_plane(const float *src, long ns, const float *tgt, 
                    fitness_out, rmse_out, iters_out, ncorr_out);
 }
 
+/* ------------------------------------------- global registration (f3) -- */
+/* compute_fpfh_feature (preprocessing/registration.py:17-20): Open3D's ComputePairFeatures /
+ * ComputeSPFHFeature / ComputeFPFHFeature restated; hybrid neighbours in canonical (d2, index) order. */
+static void kpo_pair_features(const double *p1, const double *n1, const double *p2, const double *n2, double *f)
+{
+    double d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+    double len = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+    f[0] = f[1] = f[2] = 0.0;
+    if (len == 0.0) return;
+    double a[3] = {n1[0], n1[1], n1[2]}, b[3] = {n2[0], n2[1], n2[2]};
+    double angle1 = ((a[0] * d[0] + a[1] * d[1]) + a[2] * d[2]) / len;
+    double angle2 = ((b[0] * d[0] + b[1] * d[1]) + b[2] * d[2]) / len;
+    if (acos(fabs(angle1)) > acos(fabs(angle2))) {
+        for (int c = 0; c < 3; ++c) { double t = a[c]; a[c] = b[c]; b[c] = t; d[c] = -d[c]; }
+        f[2] = -angle2;
+    } else f[2] = angle1;
+    double v[3] = {d[1] * a[2] - d[2] * a[1], d[2] * a[0] - d[0] * a[2], d[0] * a[1] - d[1] * a[0]};
+    double vn = sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+    if (vn == 0.0) { f[2] = 0.0; return; }
+    for (int c = 0; c < 3; ++c) v[c] /= vn;
+    double w[3] = {a[1] * v[2] - a[2] * v[1], a[2] * v[0] - a[0] * v[2], a[0] * v[1] - a[1] * v[0]};
+    f[1] = (v[0] * b[0] + v[1] * b[1]) + v[2] * b[2];
+    f[0] = atan2((w[0] * b[0] + w[1] * b[1]) + w[2] * b[2], (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]);
+}
+static int kpo_bin11(double x) { int h = (int)floor(x); return h < 0 ? 0 : (h > 10 ? 10 : h); }
+KPO_API int kpo_fpfh(const float *pts, const float *nrm, long n, double radius, int max_nn, double *feat /* [n][33] */)
+{
+    if (max_nn < 1 || !(radius > 0)) return -1;
+    kpo_grid_t g;
+    kpo_grid_build(&g, pts, n, radius);
+    double r2 = radius * radius;
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n ? n : 1) * (size_t)max_nn);
+    double *d2 = (double *)malloc(sizeof(double) * (size_t)(n ? n : 1) * (size_t)max_nn);
+    int *cnt = (int *)calloc((size_t)(n ? n : 1), sizeof(int));
+    double *spfh = (double *)calloc((size_t)(n ? n : 1) * 33, sizeof(double));
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < n; ++i) {
+        if (isnan(pts[3 * i])) continue;
+        kpo_query(&g, pts + 3 * i, max_nn, r2, d2 + (size_t)i * max_nn, idx + (size_t)i * max_nn, &cnt[i]);
+        int c = cnt[i];
+        if (c <= 1) continue;
+        double p1[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]}, n1[3] = {nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]};
+        double incr = 100.0 / (double)(c - 1);
+        double *h = spfh + (size_t)i * 33;
+        for (int t = 1; t < c; ++t) {
+            long j = idx[(size_t)i * max_nn + t];
+            double p2[3] = {pts[3 * j], pts[3 * j + 1], pts[3 * j + 2]}, n2[3] = {nrm[3 * j], nrm[3 * j + 1], nrm[3 * j + 2]};
+            double f[3];
+            kpo_pair_features(p1, n1, p2, n2, f);
+            h[kpo_bin11(11.0 * (f[0] + M_PI) / (2.0 * M_PI))] += incr;
+            h[11 + kpo_bin11(11.0 * (f[1] + 1.0) * 0.5)] += incr;
+            h[22 + kpo_bin11(11.0 * (f[2] + 1.0) * 0.5)] += incr;
+        }
+    }
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < n; ++i) {
+        double *f = feat + (size_t)i * 33;
+        for (int j = 0; j < 33; ++j) f[j] = 0.0;
+        int c = cnt[i];
+        if (c <= 1) continue;
+        double sum[3] = {0, 0, 0};
+        for (int t = 1; t < c; ++t) {
+            double dist = d2[(size_t)i * max_nn + t];
+            if (dist == 0.0) continue;
+            const double *sp = spfh + (size_t)idx[(size_t)i * max_nn + t] * 33;
+            for (int j = 0; j < 33; ++j) { double val = sp[j] / dist; sum[j / 11] += val; f[j] += val; }
+        }
+        for (int q = 0; q < 3; ++q) if (sum[q] != 0.0) sum[q] = 100.0 / sum[q];
+        for (int j = 0; j < 33; ++j) f[j] = f[j] * sum[j / 11] + spfh[(size_t)i * 33 + j];
+    }
+    free(idx); free(d2); free(cnt); free(spfh);
+    kpo_grid_free(&g);
+    return 0;
+}
+/* the two KD-tree searches inside registration_ransac_based_on_feature_matching: exact 1-NN in feature
+ * space, squared L2 in double summed in dimension order, ties to the lower index */
+KPO_API void kpo_feature_match(const double *fa, long na, const double *fb, long nb, int dim, int32_t *nn, double *nn_d2)
+{
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < na; ++i) {
+        double best = INFINITY; int32_t bi = -1;
+        for (long t = 0; t < nb; ++t) {
+            double s = 0.0;
+            for (int j = 0; j < dim; ++j) { double d = fa[(size_t)i * dim + j] - fb[(size_t)t * dim + j]; s += d * d; }
+            if (s < best) { best = s; bi = (int32_t)t; }
+        }
+        nn[i] = bi;
+        if (nn_d2) nn_d2[i] = best;
+    }
+}
+/* RegistrationRANSACBasedOnCorrespondence (second half of registration_ransac_based_on_feature_matching,
+ * preprocessing/registration.py:50-57): sequential over the hypothesis index with the counter-based sampler */
+KPO_API int kpo_ransac_correspondence(const float *src, const float *tgt, const int32_t *corres, long m, double max_corr,
+                                      int ransac_n, double edge_sim, double dist_thr, int max_iter, double confidence,
+                                      uint64_t seed, double *T_out, double *fitness_out, double *rmse_out, int32_t *best_iter_out,
+                                      int64_t *validated_out)
+{
+    memset(T_out, 0, sizeof(double) * 16);
+    T_out[0] = T_out[5] = T_out[10] = T_out[15] = 1;
+    *fitness_out = 0; *rmse_out = 0; *best_iter_out = -1; *validated_out = 0;
+    if (ransac_n < 3 || ransac_n > 8 || !(max_corr > 0)) return -1;
+    if (m < ransac_n) return 0;
+    double max_d2 = max_corr * max_corr, best_fit = 0, best_rmse = 0, exit_itr = (double)max_iter;
+    /* validity and scores of every hypothesis (the early exit only skips the comparison, as on the device, so that
+     * `validated` counts the same thing) */
+    char *valid = (char *)calloc((size_t)(max_iter ? max_iter : 1), 1);
+    double *Ts = (double *)malloc(sizeof(double) * 16 * (size_t)(max_iter ? max_iter : 1));
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int h = 0; h < max_iter; ++h) {
+        double s[8][3], t[8][3];
+        for (int j = 0; j < ransac_n; ++j) {
+            long c = (long)(kpo_rng(seed, (uint64_t)h, (uint64_t)j) % (uint64_t)m);
+            for (int d = 0; d < 3; ++d) { s[j][d] = src[3 * (long)corres[2 * c] + d]; t[j][d] = tgt[3 * (long)corres[2 * c + 1] + d]; }
+        }
+        int ok = 1;
+        if (edge_sim > 0)
+            for (int i = 0; i < ransac_n && ok; ++i) for (int j = i + 1; j < ransac_n; ++j) {
+                double a0 = s[i][0] - s[j][0], a1 = s[i][1] - s[j][1], a2 = s[i][2] - s[j][2];
+                double b0 = t[i][0] - t[j][0], b1 = t[i][1] - t[j][1], b2 = t[i][2] - t[j][2];
+                double ds = sqrt((a0 * a0 + a1 * a1) + a2 * a2), dt = sqrt((b0 * b0 + b1 * b1) + b2 * b2);
+                if (ds < dt * edge_sim || dt < ds * edge_sim) { ok = 0; break; }
+            }
+        if (!ok) continue;
+        double *T = Ts + 16 * (size_t)h;
+        kpo_umeyama(&s[0][0], &t[0][0], ransac_n, T);
+        if (dist_thr > 0)
+            for (int j = 0; j < ransac_n; ++j) {
+                double x = ((T[0] * s[j][0] + T[1] * s[j][1]) + T[2] * s[j][2]) + T[3];
+                double y = ((T[4] * s[j][0] + T[5] * s[j][1]) + T[6] * s[j][2]) + T[7];
+                double z = ((T[8] * s[j][0] + T[9] * s[j][1]) + T[10] * s[j][2]) + T[11];
+                double e0 = x - t[j][0], e1 = y - t[j][1], e2 = z - t[j][2];
+                if (sqrt((e0 * e0 + e1 * e1) + e2 * e2) > dist_thr) { ok = 0; break; }
+            }
+        valid[h] = (char)ok;
+    }
+    for (int h = 0; h < max_iter; ++h) {
+        if (!valid[h]) continue;
+        ++*validated_out;
+        if ((double)h >= exit_itr) continue;
+        const double *T = Ts + 16 * (size_t)h;
+        long good = 0; double err2 = 0;
+        for (long c = 0; c < m; ++c) {
+            const float *sp = src + 3 * (long)corres[2 * c], *tp = tgt + 3 * (long)corres[2 * c + 1];
+            double x = ((T[0] * sp[0] + T[1] * sp[1]) + T[2] * sp[2]) + T[3];
+            double y = ((T[4] * sp[0] + T[5] * sp[1]) + T[6] * sp[2]) + T[7];
+            double z = ((T[8] * sp[0] + T[9] * sp[1]) + T[10] * sp[2]) + T[11];
+            double e0 = x - tp[0], e1 = y - tp[1], e2 = z - tp[2];
+            double d2 = (e0 * e0 + e1 * e1) + e2 * e2;
+            if (d2 < max_d2) { ++good; err2 += d2; }
+        }
+        double fit = good ? (double)good / (double)m : 0.0, rmse = good ? sqrt(err2 / (double)good) : 0.0;
+        if (fit > best_fit || (fit == best_fit && rmse < best_rmse)) {
+            best_fit = fit; best_rmse = rmse; *best_iter_out = h;
+            memcpy(T_out, T, sizeof(double) * 16);
+            if (confidence < 1.0) {
+                double k_est = log(1.0 - confidence) / log(1.0 - pow(fit, (double)ransac_n));
+                if (k_est < exit_itr) exit_itr = ceil(k_est);
+            }
+        }
+    }
+    *fitness_out = best_fit; *rmse_out = best_rmse;
+    free(valid); free(Ts);
+    return 0;
+}
+
 KPO_API int kpo_num_threads(void)
 {
 #ifdef _OPENMP

@@ -327,6 +327,51 @@ def icp_colored(src, src_colors, tgt, tgt_colors, tgt_normals, max_corr, init=No
     return _icp(2, src, tgt, tgt_normals, s_int, t_int, t_grad, lambda_geometric, max_corr, init, max_iter, rel_fit, rel_rmse)
 
 
+def fpfh(pts, normals, radius, max_nn):
+    """compute_fpfh_feature (preprocessing/registration.py:17-20): float64 [n, 33]."""
+    pts, nrm = _f32(pts), _f32(normals)
+    feat = np.zeros((pts.shape[0], 33), np.float64)
+    if lib().kpo_fpfh(_p(pts), _p(nrm), C.c_long(pts.shape[0]), C.c_double(radius), C.c_int(max_nn), _p(feat)) != 0:
+        raise ValueError("oracle fpfh: bad arguments")
+    return feat
+
+
+def feature_match(fa, fb):
+    fa = np.ascontiguousarray(fa, dtype=np.float64)
+    fb = np.ascontiguousarray(fb, dtype=np.float64)
+    nn = np.zeros((fa.shape[0],), np.int32)
+    d2 = np.zeros((fa.shape[0],), np.float64)
+    lib().kpo_feature_match(_p(fa), C.c_long(fa.shape[0]), _p(fb), C.c_long(fb.shape[0]), C.c_int(fa.shape[1]), _p(nn), _p(d2))
+    return nn, d2
+
+
+def mutual_correspondences(nn_st, nn_ts, mutual_filter=True, ransac_n=3):
+    """Correspondence set of registration_ransac_based_on_feature_matching: i -> nn(i); with the mutual filter only
+    pairs that pick each other, unless fewer than 3 * ransac_n survive (then the unfiltered set)."""
+    i = np.arange(len(nn_st), dtype=np.int32)
+    all_c = np.stack([i, nn_st.astype(np.int32)], axis=1)
+    if not mutual_filter:
+        return all_c
+    keep = nn_ts[nn_st] == i
+    mut = all_c[keep]
+    return mut if len(mut) >= ransac_n * 3 else all_c
+
+
+def ransac_correspondence(src, tgt, corres, max_corr, ransac_n=3, edge_sim=0.95, dist_thr=None, max_iter=250000,
+                          confidence=0.999, seed=1234):
+    src, tgt = _f32(src), _f32(tgt)
+    cor = np.ascontiguousarray(corres, dtype=np.int32).reshape(-1, 2)
+    T = np.zeros(16, np.float64)
+    fit, rmse, best, val = C.c_double(), C.c_double(), C.c_int32(), C.c_int64()
+    rc = lib().kpo_ransac_correspondence(_p(src), _p(tgt), _p(cor), C.c_long(cor.shape[0]), C.c_double(max_corr), C.c_int(ransac_n),
+                                         C.c_double(edge_sim), C.c_double(max_corr if dist_thr is None else dist_thr),
+                                         C.c_int(max_iter), C.c_double(confidence), C.c_uint64(seed), _p(T), C.byref(fit),
+                                         C.byref(rmse), C.byref(best), C.byref(val))
+    if rc != 0:
+        raise ValueError("oracle ransac_correspondence: bad arguments")
+    return {"T": T.reshape(4, 4), "fitness": fit.value, "rmse": rmse.value, "best_iter": best.value, "validated": val.value}
+
+
 # ------------------------------------------------------------ compositions --
 def filter_outliers(pts, nb_neighbors=200, std_ratio=3.0, voxel_size=0.02):
     """preprocessing/filtering.py:12-25 restated on arrays: voxel -> SOR, returns kept points."""

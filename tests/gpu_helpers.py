@@ -235,3 +235,31 @@ def color_gradient(ctx, xyz, colors, normals, radius, max_nn=30):
     out = ctx.empty(d.shape, np.float32)
     ctx.check(ctx.lib.kp_color_gradient(ctx.handle, d.ptr, dc.ptr, dn.ptr, d.shape[0], float(radius), max_nn, out.ptr))
     return out.to_host()
+
+
+def fpfh(ctx, xyz, normals, radius, max_nn):
+    d, dn = ctx.to_device(xyz, np.float32), ctx.to_device(normals, np.float32)
+    out = ctx.empty((d.shape[0], 33), np.float64)
+    ctx.check(ctx.lib.kp_fpfh(ctx.handle, d.ptr, dn.ptr, d.shape[0], float(radius), max_nn, out.ptr))
+    return out.to_host()
+
+
+def feature_match(ctx, fa, fb):
+    da, db = ctx.to_device(fa, np.float64), ctx.to_device(fb, np.float64)
+    nn = ctx.empty((da.shape[0],), np.int32)
+    d2 = ctx.empty((da.shape[0],), np.float64)
+    ctx.check(ctx.lib.kp_feature_match(ctx.handle, da.ptr, da.shape[0], db.ptr, db.shape[0], 33, nn.ptr, d2.ptr))
+    return nn.to_host(), d2.to_host()
+
+
+def ransac_correspondence(ctx, src, tgt, corres, max_corr, ransac_n=3, edge_sim=0.95, dist_thr=None, max_iter=250000,
+                          confidence=0.999, seed=1234):
+    ds, dt = ctx.to_device(src, np.float32), ctx.to_device(tgt, np.float32)
+    dc = ctx.to_device(np.ascontiguousarray(corres, np.int32).reshape(-1, 2), np.int32)
+    T = np.zeros(16)
+    fit, rmse, best, val = C.c_double(), C.c_double(), C.c_int32(), C.c_int64()
+    ctx.check(ctx.lib.kp_ransac_correspondence(ctx.handle, ds.ptr, ds.shape[0], dt.ptr, dt.shape[0], dc.ptr, dc.shape[0],
+                                               float(max_corr), ransac_n, float(edge_sim), float(max_corr if dist_thr is None else dist_thr),
+                                               max_iter, float(confidence), seed, T.ctypes.data_as(C.POINTER(C.c_double)),
+                                               C.byref(fit), C.byref(rmse), C.byref(best), C.byref(val)))
+    return {"T": T.reshape(4, 4), "fitness": fit.value, "rmse": rmse.value, "best_iter": best.value, "validated": val.value}

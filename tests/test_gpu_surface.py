@@ -107,8 +107,6 @@ def test_point_to_plane_registration_matches_oracle(oracle):
     assert np.abs(T[:3, :3] - D[:3, :3]).max() < 5e-3 and np.abs(T[:3, 3] - D[:3, 3]).max() < 5.0
     plain = registration.execute_point_to_plane_registration(PointCloud(master), PointCloud(sub), np.eye(4))
     assert np.array_equal(plain, T)
-    with pytest.raises(NotImplementedError):
-        registration.execute_global_registration(PointCloud(master), PointCloud(sub))
 
 
 def test_rgbd_to_pointcloud_and_formats(oracle, tmp_path):

@@ -2,7 +2,7 @@
 Each setting runs in a fresh process (the knobs are read once)."""
 import os, subprocess, sys, json
 import numpy as np
-sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests'))
 
 def child():
     import ctypes as C
