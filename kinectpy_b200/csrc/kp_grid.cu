@@ -265,6 +265,7 @@ struct KnnParams {
     const int32_t *qlist; const int32_t *qcount;   // visit only these query positions (rows of qpts)
     uint8_t *strag_flags;                          // thread kernel: flags[q] = 1 for queries it could not certify
     const float4 *qpts;                            // self-query source rows (level-0 cell-sorted array)
+    int32_t *dbg;                                  // optional [8] tally of the reasons level 1 hands a query on (KP_DEBUG_KNN)
 };
 
 __device__ __forceinline__ bool kq_less(double d, int i, double td, int ti) { return d < td || (d == td && i < ti); }
@@ -955,13 +956,22 @@ __global__ void __launch_bounds__(HQ_THREADS) k_knn_hist(const __grid_constant__
     if (p.mean) p.mean[row] = cnt > 0 ? __ddiv_rn(acc, (double)cnt) : -1.0;
 }
 
-// ---- warp-per-query histogram select: the level-0 stragglers (isolated points and sparse fringes -- what
-// SOR is looking for) against a coarser grid.  Same two passes, but the 27-cell block holds thousands of
-// candidates, so a warp streams it 128 candidates per trip with coalesced 16-byte loads, bins with
-// shared-memory atomics into 512 bins, collects with ballots, and sorts the few survivors once.
+// ---- warp-per-query best-first histogram select: the level-0 stragglers (isolated points and sparse fringes
+// -- what SOR is looking for) against a coarser grid.  Their k-th neighbour can be a metre away, so the block
+// to search is found, not assumed:
+//   (1) grow a cube of cells around the query, COUNTING points through column lookups only (no point is
+//       read), until it holds k of them;
+//   (2) histogram the fp32 distances of that cube's points: the bin where the count reaches k is a tight
+//       upper bound U on the k-th distance (those are real points);
+//   (3) histogram every cell that reaches inside the ball of radius U (columns and z-spans pruned by their
+//       distance to the query), find the bin b of the k-th distance, and (4) collect bins <= b.
+// The few survivors are sorted once and evaluated exactly in double, as in the thread kernel.  A warp
+// streams candidate runs with coalesced 16-byte loads, four in flight per lane; bins are shared-memory
+// atomics over 512 bins (few collisions at this fan-out).
 constexpr int WH_WARPS = 4;
 constexpr int WH_NB = 512;
 constexpr int WH_CAP = 128;
+constexpr int WH_RMAX = 7;            // cube radius (cells) of step 1; the ball search then needs at most 15
 
 __device__ __forceinline__ void wh_sort(unsigned long long *a, int n2, int lane)
 {
@@ -977,7 +987,72 @@ __device__ __forceinline__ void wh_sort(unsigned long long *a, int n2, int lane)
         }
 }
 
-__global__ void __launch_bounds__(WH_WARPS * 32) k_knn_whist(const __grid_constant__ KnnParams p)
+// [start,end) of the part of column (dx, dy) of the cube of radius R that can hold a point with d2 <= budget
+// (fp32, conservative, monotone in budget); R <= 15 so that a z-span fits two cell-map words
+__device__ __forceinline__ int2 wh_column(const KpGridDev &g, const HqGeom &G, int dx, int dy, int R, float budget)
+{
+    const float gx = hq_gap(G, 0, dx), gy = hq_gap(G, 1, dy);
+    const float zb = budget - (gx * gx + gy * gy);
+    if (!(zb >= 0.0f)) return make_int2(0, 0);
+    const float reach = sqrtf(zb) * 1.000001f, fR = (float)R;
+    const int jlo = reach >= G.flo[2] ? (int)fminf((reach - G.flo[2]) / G.fcs + 1.0f, fR) : 0;
+    const int jhi = reach >= G.fhi[2] ? (int)fminf((reach - G.fhi[2]) / G.fcs + 1.0f, fR) : 0;
+    return kp_span_range(g, G.cx + dx, G.cy + dy, G.cz - jlo, G.cz + jhi);
+}
+
+// visits every candidate of the cube of radius R within `budget` of the query: fn(valid, position, point), warp-uniform
+template <class F>
+__device__ __forceinline__ void wh_visit(const KpGridDev &g, const HqGeom &G, int R, float budget, int lane, F &&fn)
+{
+    const int side = 2 * R + 1, ncol = side * side;
+    for (int c0 = 0; c0 < ncol; c0 += 32) {
+        const int c = c0 + lane;
+        int2 rr = make_int2(0, 0);
+        if (c < ncol) rr = wh_column(g, G, c / side - R, c % side - R, R, budget);
+        for (unsigned mrow = __ballot_sync(KP_FULL, rr.y > rr.x); mrow;) {
+            const int j = __ffs(mrow) - 1;
+            mrow &= mrow - 1;
+            const int ra = __shfl_sync(KP_FULL, rr.x, j), rb = __shfl_sync(KP_FULL, rr.y, j);
+            for (int t = ra + lane; t - lane < rb; t += 128) {
+                const float4 c0p = __ldg(g.pts + min(t, rb - 1));
+                const float4 c1p = __ldg(g.pts + min(t + 32, rb - 1));
+                const float4 c2p = __ldg(g.pts + min(t + 64, rb - 1));
+                const float4 c3p = __ldg(g.pts + min(t + 96, rb - 1));
+                fn(t < rb, t, c0p);
+                if (t - lane + 32 < rb) fn(t + 32 < rb, t + 32, c1p);
+                if (t - lane + 64 < rb) fn(t + 64 < rb, t + 64, c2p);
+                if (t - lane + 96 < rb) fn(t + 96 < rb, t + 96, c3p);
+            }
+        }
+    }
+}
+
+// bin in which the running count of hist reaches k (each lane owns WH_NB / 32 consecutive bins); -1 if never.
+// cum = count up to and including that bin (or the total)
+__device__ __forceinline__ int wh_select(const unsigned int *hist, int k, int lane, int &cum)
+{
+    constexpr int PER = WH_NB / 32;
+    int s = 0;
+    for (int j = 0; j < PER; ++j) s += (int)hist[lane * PER + j];
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(KP_FULL, inc, o); if (lane >= o) inc += v; }
+    const int tot = __shfl_sync(KP_FULL, inc, 31);
+    const unsigned reach = __ballot_sync(KP_FULL, inc >= k);
+    int bb = -1, mm = tot;
+    if (reach) {
+        const int L = __ffs(reach) - 1;
+        if (lane == L) {
+            int c = inc - s;
+            for (int j = 0; j < PER; ++j) { c += (int)hist[lane * PER + j]; if (c >= k) { bb = lane * PER + j; mm = c; break; } }
+        }
+        bb = __shfl_sync(KP_FULL, bb, L); mm = __shfl_sync(KP_FULL, mm, L);
+    }
+    cum = mm;
+    return bb;
+}
+
+__global__ void __launch_bounds__(WH_WARPS * 32) k_knn_wbf(const __grid_constant__ KnnParams p)
 {
     __shared__ unsigned int s_hist[WH_WARPS][WH_NB];
     __shared__ unsigned long long s_buf[WH_WARPS][WH_CAP];
@@ -998,108 +1073,121 @@ __global__ void __launch_bounds__(WH_WARPS * 32) k_knn_whist(const __grid_consta
         const int64_t row = __float_as_int(me.w);
         const double qx = (double)me.x, qy = (double)me.y, qz = (double)me.z;
         HqGeom G;
-        hq_geom(g, qx, qy, qz, p.r2cap, WH_NB, true, 1, G);
-        // the 27 cells, z-rows merged (lanes 0, 3, .., 24 hold one contiguous run each)
-        int a, b;
-        {
-            int2 r = make_int2(0, 0);
-            if (lane < 27) r = kp_cell_range(g, G.cx + lane / 9 - 1, G.cy + (lane / 3) % 3 - 1, G.cz + lane % 3 - 1);
-            const bool ne = r.y > r.x;
-            a = ne ? r.x : 0x7fffffff; b = ne ? r.y : 0;
-            const int a1 = __shfl_down_sync(KP_FULL, a, 1), b1 = __shfl_down_sync(KP_FULL, b, 1);
-            const int a2 = __shfl_down_sync(KP_FULL, a, 2), b2 = __shfl_down_sync(KP_FULL, b, 2);
-            if (lane < 27 && lane % 3 == 0) { a = min(a, min(a1, a2)); b = max(b, max(b1, b2)); if (b == 0) a = 0; }
-            else { a = 0; b = 0; }
-        }
-        const unsigned rows = __ballot_sync(KP_FULL, b > a);
-        for (int j = lane; j < WH_NB; j += 32) hist[j] = 0;
-        __syncwarp();
-        // ---- pass 1
-        for (unsigned mrow = rows; mrow;) {
-            const int j = __ffs(mrow) - 1;
-            mrow &= mrow - 1;
-            const int ra = __shfl_sync(KP_FULL, a, j), rb = __shfl_sync(KP_FULL, b, j);
-            for (int t = ra + lane; t < rb; t += 128) {
-                const float4 c0 = __ldg(g.pts + t);
-                const float4 c1 = __ldg(g.pts + min(t + 32, rb - 1));
-                const float4 c2 = __ldg(g.pts + min(t + 64, rb - 1));
-                const float4 c3 = __ldg(g.pts + min(t + 96, rb - 1));
-                const int b0 = hq_bin(hq_d32(me.x, me.y, me.z, c0), G.scale), b1 = hq_bin(hq_d32(me.x, me.y, me.z, c1), G.scale);
-                const int b2 = hq_bin(hq_d32(me.x, me.y, me.z, c2), G.scale), b3 = hq_bin(hq_d32(me.x, me.y, me.z, c3), G.scale);
-                if ((unsigned)b0 < (unsigned)WH_NB) atomicAdd(hist + b0, 1u);
-                if (t + 32 < rb && (unsigned)b1 < (unsigned)WH_NB) atomicAdd(hist + b1, 1u);
-                if (t + 64 < rb && (unsigned)b2 < (unsigned)WH_NB) atomicAdd(hist + b2, 1u);
-                if (t + 96 < rb && (unsigned)b3 < (unsigned)WH_NB) atomicAdd(hist + b3, 1u);
-            }
-        }
-        __syncwarp();
-        // ---- the bin of the k-th distance: each lane owns 16 consecutive bins
-        int bsel, m, tot;
-        {
-            constexpr int PER = WH_NB / 32;
-            int s = 0;
-            for (int j = 0; j < PER; ++j) s += (int)hist[lane * PER + j];
-            int inc = s;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(KP_FULL, inc, o); if (lane >= o) inc += v; }
-            tot = __shfl_sync(KP_FULL, inc, 31);
-            const unsigned reach = __ballot_sync(KP_FULL, inc >= k);
-            int bb = WH_NB - 1, mm = tot;
-            if (reach) {
-                const int L = __ffs(reach) - 1;
-                if (lane == L) {
-                    int cum = inc - s;
-                    for (int j = 0; j < PER; ++j) { cum += (int)hist[lane * PER + j]; if (cum >= k) { bb = lane * PER + j; mm = cum; break; } }
+        hq_geom(g, qx, qy, qz, 0.0, WH_NB, true, 1, G);
+        const double cs = g.cell * (1.0 - 1.0 / 1048576.0);
+        const double capw = p.r2cap > 0 ? p.r2cap * (1.0 + 2e-6) : INFINITY;   // fp32 d2 of every eligible candidate is below
+        bool fail = false;
+        // ---- (1) smallest cube with k points (or the cube that covers the whole radius cap)
+        int r = 0;
+        bool cap_binding = false;        // the cube covers the cap ball: nothing eligible lies outside it
+        for (;;) {
+            ++r;
+            if (r > WH_RMAX) { fail = true; if (p.dbg && lane == 0) atomicAdd(p.dbg + 0, 1); break; }
+            const int side = 2 * r + 1, ncol = side * side;
+            int cntc = 0;
+            for (int c0 = 0; c0 < ncol; c0 += 32) {
+                const int c = c0 + lane;
+                if (c < ncol) {
+                    const int2 rr = kp_span_range(g, G.cx + c / side - r, G.cy + c % side - r, G.cz - r, G.cz + r);
+                    cntc += rr.y - rr.x;
                 }
-                bb = __shfl_sync(KP_FULL, bb, L); mm = __shfl_sync(KP_FULL, mm, L);
             }
-            bsel = bb; m = mm;
+            cntc = kq_warp_sum(cntc);
+            const double inside = (double)r * cs;            // every point closer than this lies in the cube
+            if (p.r2cap > 0 && inside * inside >= capw) { cap_binding = true; break; }
+            if (cntc >= k) break;
         }
-        const bool all = (m == tot);
-        bool fail = m > WH_CAP || (m < k && !G.cap_binding);
-        int n = 0;
+        int n = 0, bsel = -1, m = 0;
+        double U2 = 0.0;
+        float scale = 0.0f;
+        bool all = false;
         if (!fail) {
-            // ---- pass 2: collect bins <= bsel
-            for (unsigned mrow = rows; mrow;) {
-                const int j = __ffs(mrow) - 1;
-                mrow &= mrow - 1;
-                const int ra = __shfl_sync(KP_FULL, a, j), rb = __shfl_sync(KP_FULL, b, j);
-                for (int t0 = ra; t0 < rb; t0 += 32) {
-                    const int t = t0 + lane;
-                    const bool v = t < rb;
-                    const float4 c = __ldg(g.pts + (v ? t : ra));
-                    const float d = hq_d32(me.x, me.y, me.z, c);
-                    const bool pass = v && (unsigned)hq_bin(d, G.scale) <= (unsigned)bsel;
-                    const unsigned pm = __ballot_sync(KP_FULL, pass);
-                    if (pass) buf[n + __popc(pm & lt)] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)t;
-                    n += __popc(pm);
-                }
+            // ---- (2) k-th smallest distance among the cube's points -> upper bound U2 on the k-th distance^2
+            const double far = (double)(r + 1) * g.cell;      // no point of the cube is farther than sqrt(3) * far
+            double range = fmin(3.0 * far * far, capw);
+            scale = (float)((double)(WH_NB - 1) / range);
+            for (int j = lane; j < WH_NB; j += 32) hist[j] = 0;
+            __syncwarp();
+            wh_visit(g, G, r, INFINITY, lane, [&](bool v, int, const float4 &c) {
+                const int bj = hq_bin(hq_d32(me.x, me.y, me.z, c), scale);
+                if (v && (unsigned)bj < (unsigned)WH_NB) atomicAdd(hist + bj, 1u);
+            });
+            __syncwarp();
+            int cum;
+            const int b1 = wh_select(hist, k, lane, cum);
+            if (b1 >= 0) U2 = fmin(((double)b1 + 1.0) / (double)scale, capw);
+            else if (cap_binding) U2 = capw;                  // fewer than k inside the cap: all of them are wanted
+            else { fail = true; if (p.dbg && lane == 0) atomicAdd(p.dbg + 1, 1); }   // (cannot happen: the cube holds k points within range)
+            cap_binding = p.r2cap > 0 && U2 >= capw;          // step 3 visits the whole cap ball: nothing eligible is missed
+        }
+        // ---- (3) + (4), retried once with shifted bin edges when the k-th distance sits within rounding of an
+        // edge (the certificate then cannot tell collected from uncollected; ~1e-3 of the queries)
+        bool done = false;
+        for (int attempt = 0; attempt < 2 && !fail && !done; ++attempt) {
+            // (3) histogram of everything within U2; the ball needs cells up to R2 away
+            int R2 = (int)ceil(sqrt(U2) / cs);
+            if (R2 < 1) R2 = 1;
+            if (R2 > 15) { fail = true; if (p.dbg && lane == 0) atomicAdd(p.dbg + 2, 1); break; }   // z-span would not fit the two-word cell-map lookup
+            const float budget = hq_budget(U2);
+            scale = (float)((double)(WH_NB - 1) / U2 * (attempt ? 0.9371 : 1.0));
+            n = 0;
+            __syncwarp();
+            for (int j = lane; j < WH_NB; j += 32) hist[j] = 0;
+            __syncwarp();
+            wh_visit(g, G, R2, budget, lane, [&](bool v, int, const float4 &c) {
+                const int bj = hq_bin(hq_d32(me.x, me.y, me.z, c), scale);
+                if (v && (unsigned)bj < (unsigned)WH_NB) atomicAdd(hist + bj, 1u);
+            });
+            __syncwarp();
+            bsel = wh_select(hist, k, lane, m);
+            all = bsel < 0;                                // fewer than k in range: take them all
+            if (bsel < 0) bsel = WH_NB - 1;
+            if (m > WH_CAP || (all && !cap_binding)) {
+                fail = true;
+                if (p.dbg && lane == 0) atomicAdd(p.dbg + (m > WH_CAP ? 3 : 4), 1);
+                break;
             }
+            // (4) collect bins <= bsel (cells chosen by the same rule under a budget that is not larger)
+            const float budget3 = hq_budget(fmin(U2, ((double)bsel + 1.0) / (double)scale));
+            wh_visit(g, G, R2, budget3, lane, [&](bool v, int t, const float4 &c) {
+                const float d = hq_d32(me.x, me.y, me.z, c);
+                const bool pass = v && (unsigned)hq_bin(d, scale) <= (unsigned)bsel;
+                const unsigned pm = __ballot_sync(KP_FULL, pass);
+                const int pos = n + __popc(pm & lt);
+                if (pass && pos < WH_CAP) buf[pos] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)t;
+                n += __popc(pm);
+            });
+            if (n != m) { fail = true; if (p.dbg && lane == 0) atomicAdd(p.dbg + 5, 1); break; }   // cannot happen; never trust a scatter blindly
+            // ---- exact evaluation of the survivors and ONE exact sort by the canonical (d2, index) order.  (At these
+            // distances fp32 squared distances collide -- two of ~100 candidates share a float in a few percent of
+            // the queries -- so the fp32 order is only used to choose the set, never to order it.)
             int n2 = 32;
             while (n2 < n) n2 <<= 1;
-            for (int t = n + lane; t < n2; t += 32) buf[t] = ~0ull;
             __syncwarp();
-            wh_sort(buf, n2, lane);
-            // ---- exact evaluation
-            for (int t = lane; t < n; t += 32) {
-                const float4 c = __ldg(g.pts + (unsigned)buf[t]);
-                dd[t] = kp_d2(qx, qy, qz, (double)c.x, (double)c.y, (double)c.z);
-                ii[t] = __float_as_int(c.w);
+            for (int t = lane; t < n2; t += 32) {
+                if (t < n) {
+                    const float4 c = __ldg(g.pts + (unsigned)buf[t]);
+                    dd[t] = kp_d2(qx, qy, qz, (double)c.x, (double)c.y, (double)c.z);
+                    ii[t] = __float_as_int(c.w);
+                } else { dd[t] = INFINITY; ii[t] = 0x7fffffff; }
             }
             __syncwarp();
-            bool bad = false;
+            kq_sort(dd, ii, n2, lane);
             int within = 0;
-            for (int t = lane; t < n; t += 32) {
-                if (t > 0 && !hq_before(dd[t - 1], ii[t - 1], dd[t], ii[t])) bad = true;
+            for (int t = lane; t < n; t += 32)
                 if (t < k && (p.r2cap <= 0 || dd[t] < p.r2cap)) ++within;
-            }
-            bad = __any_sync(KP_FULL, bad);
-            const int cnt = kq_warp_sum(within);    // ascending order verified: the eligible entries are a prefix
+            const int cnt = kq_warp_sum(within);    // sorted ascending: the eligible entries are a prefix
             bool exact;
-            if (all && G.cap_binding) exact = true;
-            else exact = cnt == k && dd[k - 1] < hq_lower_edge(bsel, G.scale) && (G.cap_binding || dd[k - 1] < G.Rcert2);
-            fail = bad || !exact;
-            if (!fail && lane == 0) kq_finalize(p, row, cnt, dd, ii, 1);
+            if (all && cap_binding) exact = true;
+            else exact = cnt == k && dd[k - 1] < hq_lower_edge(bsel, scale) && dd[k - 1] < U2;
+            if (exact) {
+                done = true;
+                if (lane == 0) kq_finalize(p, row, cnt, dd, ii, 1);
+            } else if (attempt == 1 || cnt != k) {
+                fail = true;
+                if (p.dbg && lane == 0) atomicAdd(p.dbg + 7, 1);
+            }
+            __syncwarp();
         }
         if (fail && lane == 0) p.strag_flags[q] = 1;
         __syncwarp();
@@ -1158,7 +1246,7 @@ int knn_launch(kp_ctx *ctx, KnnParams &p, const char *name, const float *d_xyz =
     double out_b = p.mode == KQ_MODE_RADIUS ? 4.0 : p.mode == KQ_MODE_NORMALS ? 12.0 + 12.0
                    : (p.idx ? 4.0 * p.k : 0.0) + (p.d2 ? 8.0 * p.k : 0.0) + (p.count ? 4.0 : 0.0) + (p.mean ? 8.0 : 0.0);
     KP_PROFB(ctx, name, (double)p.g.npts * 16.0 + (double)p.nq * (out_b + (p.queries ? 12.0 : 0.0)));
-    p.qlist = nullptr; p.qcount = nullptr; p.strag_flags = nullptr;
+    p.qlist = nullptr; p.qcount = nullptr; p.strag_flags = nullptr; p.dbg = nullptr;
     p.qpts = p.g.pts;
     const bool fast = !p.queries && p.mode != KQ_MODE_RADIUS && p.k <= HQ_KMAX;
     if (!fast) return knn_launch_warp(ctx, p, p.nq);
@@ -1210,13 +1298,25 @@ int knn_launch(kp_ctx *ctx, KnnParams &p, const char *name, const float *d_xyz =
         p.g = kp_grid_dev(gl);
         KP_TRY(kp_ws(ctx, (size_t)n_strag, &listB));
         KP_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)nq0, ctx->stream));
+        if (getenv("KP_DEBUG_KNN")) {
+            KP_TRY(kp_ws(ctx, 8, &p.dbg));
+            KP_CUDA(ctx, cudaMemsetAsync(p.dbg, 0, 8 * sizeof(int32_t), ctx->stream));
+        }
         {
             KP_PROF(ctx, "knn_level1");
             int64_t blocks = ((int64_t)n_strag + WH_WARPS - 1) / WH_WARPS;
             const int64_t cap_blocks = (int64_t)ctx->sm_count * 16;
             if (blocks > cap_blocks) blocks = cap_blocks;
-            k_knn_whist<<<(unsigned)blocks, WH_WARPS * 32, 0, ctx->stream>>>(p);
+            k_knn_wbf<<<(unsigned)blocks, WH_WARPS * 32, 0, ctx->stream>>>(p);
             KP_LAUNCH_CHECK(ctx);
+        }
+        if (p.dbg) {
+            KP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, p.dbg, 8 * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+            KP_TRY(kp_fetch_scratch(ctx, 8 * sizeof(int32_t)));
+            const int32_t *d = (const int32_t *)ctx->h_scratch;
+            fprintf(stderr, "[kp knn] level-1 hand-overs: cube>%d %d, no-bound %d, ball>15 %d, bin>cap %d, short %d, scatter %d, order %d, uncertified %d\n",
+                    WH_RMAX, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
+            p.dbg = nullptr;
         }
         int32_t n2 = 0;
         KP_TRY(knn_flag_list(ctx, nq0, flags, listB, counts + 1, &n2));

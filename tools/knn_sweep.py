@@ -29,7 +29,7 @@ def child():
         ctx.check(ctx.lib.kp_sor_mask(ctx.handle, d.ptr, n, k, 2.0, hint, keep.ptr, None, None, C.byref(kept)))
     pr = ctx.profile_read()
     out = {kk: round(v["ms"] / 2, 3) for kk, v in pr.items() if kk.startswith("knn") or kk in ("sor_knn", "radix_sort", "grid_hash")}
-    print(json.dumps({"k": k, "base": mult, "rad": os.environ.get("KP_KNN_RAD"), "kept": kept.value, "n": n, "ms": out}))
+    print(json.dumps({"k": k, "base": mult, "rad": os.environ.get("KP_KNN_RAD"), "cm": os.environ.get("KP_KNN_COARSE_MULT"), "kept": kept.value, "n": n, "ms": out}))
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
@@ -39,11 +39,12 @@ if __name__ == "__main__":
         for k in (20, 50):
             for rad in (1,):
                 for base in (1.5,):
-                    cfgs.append(dict(SW_K=k, SW_BASE=base, KP_KNN_RAD=rad))
+                    for cm in (3,):
+                        cfgs.append(dict(SW_K=k, SW_BASE=base, KP_KNN_RAD=rad, KP_KNN_COARSE_MULT=cm))
         for c in cfgs:
             env = dict(os.environ, KP_DEBUG_KNN="1", **{a: str(b) for a, b in c.items()})
             r = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-            lev = [l.split("[kp knn] ")[1] for l in r.stderr.splitlines() if "kp knn" in l][-2:]
+            lev = [l.split("[kp knn] ")[1] for l in r.stderr.splitlines() if "kp knn" in l][-3:]
             print(r.stdout.strip(), "|", "; ".join(dict.fromkeys(lev)))
             if r.returncode != 0:
                 print(r.stderr[-2000:])
