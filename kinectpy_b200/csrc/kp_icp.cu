@@ -13,6 +13,7 @@
 // max_iter+1 passes without reading anything back; passes after `done` return immediately.
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 #include "kp_grid.cuh"
 #include "kp_umeyama.cuh"
 
@@ -55,37 +56,16 @@ struct IcpParams {
 };
 
 __global__ void __launch_bounds__(256) k_icp_init(const float *src, int ns, const __grid_constant__ IcpParams p, IcpState init,
-                                                  double *out, unsigned long long *keys, int32_t *vals)
+                                                  double *out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *p.st = init;
     if (i >= ns) return;
     const double *T = init.T;
     double X = src[3 * (int64_t)i], Y = src[3 * (int64_t)i + 1], Z = src[3 * (int64_t)i + 2];
-    const double x = kp_affine(T[0], T[1], T[2], T[3], X, Y, Z);
-    const double y = kp_affine(T[4], T[5], T[6], T[7], X, Y, Z);
-    const double z = kp_affine(T[8], T[9], T[10], T[11], X, Y, Z);
-    out[3 * (int64_t)i] = x; out[3 * (int64_t)i + 1] = y; out[3 * (int64_t)i + 2] = z;
-    if (keys) {
-        // key of the target-grid cell the point starts in (clamped; NaN rows last): the passes walk the source
-        // in this order, so the lanes of a warp look up the same few cell-map words and candidate runs
-        const KpGridDev &g = p.g;
-        unsigned long long key = ~0ull >> 1;
-        if (!isnan(x) && g.dim[0] > 0) {
-            const int cx = min(max(kp_cell_coord(g, x, 0), 0), g.dim[0] - 1);
-            const int cy = min(max(kp_cell_coord(g, y, 1), 0), g.dim[1] - 1);
-            const int cz = min(max(kp_cell_coord(g, z, 2), 0), g.dim[2] - 1);
-            key = kp_cell_key(g, cx, cy, cz);
-        }
-        keys[i] = key; vals[i] = i;
-    }
-}
-__global__ void __launch_bounds__(256) k_icp_reorder(const double *in, const int32_t *order, int ns, double *out)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ns) return;
-    const int64_t j = order[i];
-    out[3 * (int64_t)i] = in[3 * j]; out[3 * (int64_t)i + 1] = in[3 * j + 1]; out[3 * (int64_t)i + 2] = in[3 * j + 2];
+    out[3 * (int64_t)i] = kp_affine(T[0], T[1], T[2], T[3], X, Y, Z);
+    out[3 * (int64_t)i + 1] = kp_affine(T[4], T[5], T[6], T[7], X, Y, Z);
+    out[3 * (int64_t)i + 2] = kp_affine(T[8], T[9], T[10], T[11], X, Y, Z);
 }
 
 __device__ bool icp_solve6(double M[6][7], double *x)
@@ -163,15 +143,30 @@ __device__ __forceinline__ int icp_nearest(const KpGridDev &g, double sx, double
         const int oi = order[k], dx = oi / 3 - 1, dy = oi % 3 - 1;
         const float gx = dx < 0 ? flo[0] : (dx > 0 ? fhi[0] : 0.0f), gy = dy < 0 ? flo[1] : (dy > 0 ? fhi[1] : 0.0f);
         if (gx * gx + gy * gy > cur) continue;
-        for (int t = rng[oi].x; t < rng[oi].y; ++t) {
-            const float4 q = __ldg(g.pts + t);
-            const float ex = fx32 - q.x, ey = fy32 - q.y, ez = fz32 - q.z;
-            if (__fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex)) > lim32) continue;
-            const double d2 = kp_d2(sx, sy, sz, (double)q.x, (double)q.y, (double)q.z);
-            const int id = __float_as_int(q.w);
-            if (d2 < r2 && (d2 < bd || (d2 == bd && id < bi))) {
-                bd = d2; bi = id; bpos = t;
-                lim32 = __double2float_ru(bd + slack); cur = __double2float_ru(bd * (1.0 + 4e-6));
+        // four candidates per trip: the loads are issued together, so a column costs one memory round trip per four
+        // candidates instead of one each (the warp stalls at the first use of a loaded value)
+        for (int t = rng[oi].x; t < rng[oi].y; t += 4) {
+            const int m = rng[oi].y - t;
+            float4 q[4];
+            q[0] = __ldg(g.pts + t);
+            q[1] = __ldg(g.pts + (m > 1 ? t + 1 : t));
+            q[2] = __ldg(g.pts + (m > 2 ? t + 2 : t));
+            q[3] = __ldg(g.pts + (m > 3 ? t + 3 : t));
+            float d32[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float ex = fx32 - q[u].x, ey = fy32 - q[u].y, ez = fz32 - q[u].z;
+                d32[u] = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (u >= m || d32[u] > lim32) continue;
+                const double d2 = kp_d2(sx, sy, sz, (double)q[u].x, (double)q[u].y, (double)q[u].z);
+                const int id = __float_as_int(q[u].w);
+                if (d2 < r2 && (d2 < bd || (d2 == bd && id < bi))) {
+                    bd = d2; bi = id; bpos = t + u;
+                    lim32 = __double2float_ru(bd + slack); cur = __double2float_ru(bd * (1.0 + 4e-6));
+                }
             }
         }
     }
@@ -489,32 +484,15 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
     for (int i = 0; i < 16; ++i) { init.T[i] = h_init16[i]; init.U[i] = (i % 5 == 0) ? 1.0 : 0.0; }
     p.pass = 0;
     {
-        // moving source = init * src, re-ordered by target-grid cell (the normal equations are sums: order-free)
+        // moving source = init * src.  (Re-ordering the source by target-grid cell was measured: the voxel order the
+        // source arrives in is already coherent, and the extra sort cost more than the lookups it saved.)
         const size_t nn = (size_t)(n_src > 0 ? n_src : 1);
-        double *tmp;
-        unsigned long long *keys, *keys_tmp, *keys_sorted;
-        int32_t *vals, *vals_tmp, *vals_sorted = nullptr;
-        KP_TRY(kp_ws(ctx, nn * 3, &tmp));
-        KP_TRY(kp_ws(ctx, nn, &keys));
-        KP_TRY(kp_ws(ctx, nn, &keys_tmp));
-        KP_TRY(kp_ws(ctx, nn, &vals));
-        KP_TRY(kp_ws(ctx, nn, &vals_tmp));
-        const bool reorder = n_src > 1024 && tgt_grid.n > 0;
-        k_icp_init<<<kp_blocks(nn, 256), 256, 0, ctx->stream>>>(d_src, (int)n_src, p, init, reorder ? tmp : p.cur,
-                                                              reorder ? keys : nullptr, vals);
+        k_icp_init<<<kp_blocks(nn, 256), 256, 0, ctx->stream>>>(d_src, (int)n_src, p, init, p.cur);
         KP_LAUNCH_CHECK(ctx);
-        if (reorder) {
-            int bits = 1;
-            while (bits < 63 && (((unsigned long long)(p.g.dim[0] - 1) << p.g.sh_x) >> bits) != 0ull) ++bits;
-            KP_TRY(kp_prim_sort_pairs_u64(ctx, n_src, bits + 1 > 63 ? 63 : bits + 1, (uint64_t *)keys, (uint64_t *)keys_tmp, vals, vals_tmp,
-                                          (uint64_t **)&keys_sorted, &vals_sorted));
-            k_icp_reorder<<<kp_blocks(nn, 256), 256, 0, ctx->stream>>>(tmp, vals_sorted, (int)n_src, p.cur);
-            KP_LAUNCH_CHECK(ctx);
-        }
         if (p.mode == ICP_COLORED && n_src > 0) {
             float *si;
             KP_TRY(kp_ws(ctx, nn, &si));
-            k_intensity<<<kp_blocks(nn, 256), 256, 0, ctx->stream>>>(extra->src_colors, n_src, reorder ? vals_sorted : nullptr, si);
+            k_intensity<<<kp_blocks(nn, 256), 256, 0, ctx->stream>>>(extra->src_colors, n_src, nullptr, si);
             KP_LAUNCH_CHECK(ctx);
             p.src_int = si;
         }
