@@ -772,18 +772,18 @@ __device__ void kq_finish_normal(const KnnParams &p, int64_t row, int cnt, doubl
     p.normals[3 * row] = (float)nr[0]; p.normals[3 * row + 1] = (float)nr[1]; p.normals[3 * row + 2] = (float)nr[2];
 }
 
-template <int NB, int R>
-__global__ void __launch_bounds__(HQ_THREADS) k_knn_hist(const __grid_constant__ KnnParams p)
+template <int NB, int R, int HQT>
+__global__ void __launch_bounds__(HQT) k_knn_hist(const __grid_constant__ KnnParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const KpGridDev &g = p.g;
     const int tid = threadIdx.x;
-    const int64_t w = (int64_t)blockIdx.x * HQ_THREADS + tid;
+    const int64_t w = (int64_t)blockIdx.x * HQT + tid;
     if (w >= p.nq) return;
     const int64_t q = w;
-    // buf[slot * HQ_THREADS], hist[bin * HQ_THREADS]: any slot pattern is bank-conflict free
+    // buf[slot * HQT], hist[bin * HQT]: any slot pattern is bank-conflict free
     unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem_raw) + tid;
-    unsigned short *hist = reinterpret_cast<unsigned short *>(smem_raw + (size_t)p.cap * HQ_THREADS * sizeof(unsigned long long)) + tid;
+    unsigned short *hist = reinterpret_cast<unsigned short *>(smem_raw + (size_t)p.cap * HQT * sizeof(unsigned long long)) + tid;
     const int k = p.k;
     const float4 me = __ldg(p.qpts + q);
     const int64_t row = __float_as_int(me.w);
@@ -796,57 +796,52 @@ __global__ void __launch_bounds__(HQ_THREADS) k_knn_hist(const __grid_constant__
     HqGeom G;
     hq_geom(g, qx, qy, qz, p.r2cap, NB, false, R, G);
 #pragma unroll
-    for (int j = 0; j < NB; ++j) hist[j * HQ_THREADS] = 0;
-    // four candidates per trip: the loads and the four distance chains are independent
+    for (int j = 0; j < NB; ++j) hist[j * HQT] = 0;
+    // HQ_U candidates per trip: the loads and the distance chains are independent, so one L1 round trip covers all of them
+    constexpr int HQ_U = 4;   // swept: 8 is slower (columns hold 10-40 candidates; longer trips waste on the tail)
     auto count = [&](const int2 rr) {
-        for (int t = rr.x; t < rr.y; t += 4) {
+        for (int t = rr.x; t < rr.y; t += HQ_U) {
             const int m = rr.y - t;
-            const float4 c0 = __ldg(g.pts + t);
-            const float4 c1 = __ldg(g.pts + (m > 1 ? t + 1 : t));
-            const float4 c2 = __ldg(g.pts + (m > 2 ? t + 2 : t));
-            const float4 c3 = __ldg(g.pts + (m > 3 ? t + 3 : t));
-            const int b0 = hq_bin(hq_d32(me.x, me.y, me.z, c0), G.scale);
-            const int b1 = hq_bin(hq_d32(me.x, me.y, me.z, c1), G.scale);
-            const int b2 = hq_bin(hq_d32(me.x, me.y, me.z, c2), G.scale);
-            const int b3 = hq_bin(hq_d32(me.x, me.y, me.z, c3), G.scale);
+            float4 c[HQ_U];
+#pragma unroll
+            for (int u = 0; u < HQ_U; ++u) c[u] = __ldg(g.pts + (m > u ? t + u : t));
+            int bj[HQ_U];
+#pragma unroll
+            for (int u = 0; u < HQ_U; ++u) bj[u] = hq_bin(hq_d32(me.x, me.y, me.z, c[u]), G.scale);
             // (shared-memory atomics were measured here: 4x slower than the plain read-modify-write)
-            if ((unsigned)b0 < (unsigned)NB) hist[b0 * HQ_THREADS]++;
-            if (m > 1 && (unsigned)b1 < (unsigned)NB) hist[b1 * HQ_THREADS]++;
-            if (m > 2 && (unsigned)b2 < (unsigned)NB) hist[b2 * HQ_THREADS]++;
-            if (m > 3 && (unsigned)b3 < (unsigned)NB) hist[b3 * HQ_THREADS]++;
+#pragma unroll
+            for (int u = 0; u < HQ_U; ++u)
+                if (m > u && (unsigned)bj[u] < (unsigned)NB) hist[bj[u] * HQT]++;
         }
     };
     int b = -1, m = 0, nput = 0;
     auto collect = [&](const int2 rr) {
-        for (int t = rr.x; t < rr.y; t += 4) {
+        for (int t = rr.x; t < rr.y; t += HQ_U) {
             const int mm = rr.y - t;
-            const float4 c0 = __ldg(g.pts + t);
-            const float4 c1 = __ldg(g.pts + (mm > 1 ? t + 1 : t));
-            const float4 c2 = __ldg(g.pts + (mm > 2 ? t + 2 : t));
-            const float4 c3 = __ldg(g.pts + (mm > 3 ? t + 3 : t));
-            const float d0 = hq_d32(me.x, me.y, me.z, c0), d1 = hq_d32(me.x, me.y, me.z, c1);
-            const float d2 = hq_d32(me.x, me.y, me.z, c2), d3 = hq_d32(me.x, me.y, me.z, c3);
-            const int b0 = hq_bin(d0, G.scale), b1 = hq_bin(d1, G.scale), b2 = hq_bin(d2, G.scale), b3 = hq_bin(d3, G.scale);
-#define HQ_PUT(bj, dj, off)                                                                                     \
-    if ((unsigned)(bj) <= (unsigned)b) {                                                                        \
-        const int slot = hist[(bj) * HQ_THREADS];                                                               \
-        hist[(bj) * HQ_THREADS] = (unsigned short)(slot + 1);                                                   \
-        if (slot < m) buf[slot * HQ_THREADS] = ((unsigned long long)__float_as_uint(dj) << 32) | (unsigned)(t + (off)); \
-        ++nput;                                                                                                 \
-    }
-            HQ_PUT(b0, d0, 0)
-            if (mm > 1) HQ_PUT(b1, d1, 1)
-            if (mm > 2) HQ_PUT(b2, d2, 2)
-            if (mm > 3) HQ_PUT(b3, d3, 3)
-#undef HQ_PUT
+            float4 c[HQ_U];
+#pragma unroll
+            for (int u = 0; u < HQ_U; ++u) c[u] = __ldg(g.pts + (mm > u ? t + u : t));
+            float dj[HQ_U];
+#pragma unroll
+            for (int u = 0; u < HQ_U; ++u) dj[u] = hq_d32(me.x, me.y, me.z, c[u]);
+#pragma unroll
+            for (int u = 0; u < HQ_U; ++u) {
+                const int bu = hq_bin(dj[u], G.scale);
+                if (mm > u && (unsigned)bu <= (unsigned)b) {
+                    const int slot = hist[bu * HQT];
+                    hist[bu * HQT] = (unsigned short)(slot + 1);
+                    if (slot < m) buf[slot * HQT] = ((unsigned long long)__float_as_uint(dj[u]) << 32) | (unsigned)(t + u);
+                    ++nput;
+                }
+            }
         }
     };
     // the bin that holds the k-th distance; the histogram becomes the scatter offsets of pass 2
     auto select_bin = [&]() {
         int cum = 0;
         for (int j = 0; j < NB; ++j) {
-            const int c = (int)hist[j * HQ_THREADS];
-            hist[j * HQ_THREADS] = (unsigned short)cum;
+            const int c = (int)hist[j * HQT];
+            hist[j * HQT] = (unsigned short)cum;
             cum += c;
             if (cum >= k) { b = j; break; }
         }
@@ -887,7 +882,7 @@ __global__ void __launch_bounds__(HQ_THREADS) k_knn_hist(const __grid_constant__
             if (ci == 9) {
                 int cum = 0;
                 for (int j = 0; j < NB; ++j) {
-                    cum += hist[j * HQ_THREADS];
+                    cum += hist[j * HQT];
                     if (cum >= k) { budget = fmin(budget, ((double)j + 1.0) / (double)G.scale); bounded = true; break; }
                 }
                 fbudget = hq_budget(budget);
@@ -905,15 +900,15 @@ __global__ void __launch_bounds__(HQ_THREADS) k_knn_hist(const __grid_constant__
     if (nput != m) { p.strag_flags[q] = 1; return; }
     // ---- order by (fp32 d2, position): entries only move inside their bin
     for (int i = 1; i < m; ++i) {
-        const unsigned long long key = buf[i * HQ_THREADS];
+        const unsigned long long key = buf[i * HQT];
         int j = i - 1;
         while (j >= 0) {
-            const unsigned long long o = buf[j * HQ_THREADS];
+            const unsigned long long o = buf[j * HQT];
             if (o <= key) break;
-            buf[(j + 1) * HQ_THREADS] = o;
+            buf[(j + 1) * HQT] = o;
             --j;
         }
-        buf[(j + 1) * HQ_THREADS] = key;
+        buf[(j + 1) * HQT] = key;
     }
     // ---- exact evaluation in that order; the canonical (d2, index) order must be strictly ascending
     const bool capped = p.r2cap > 0;
@@ -924,7 +919,7 @@ __global__ void __launch_bounds__(HQ_THREADS) k_knn_hist(const __grid_constant__
     int cnt = 0;
     bool bad = false, closed = false;
     for (int i = 0; i < m; ++i) {
-        const float4 c = __ldg(g.pts + (unsigned)buf[i * HQ_THREADS]);
+        const float4 c = __ldg(g.pts + (unsigned)buf[i * HQT]);
         const double d = kp_d2(qx, qy, qz, (double)c.x, (double)c.y, (double)c.z);
         const int id = __float_as_int(c.w);
         if (!hq_before(pd, pi, d, id)) bad = true;
@@ -1220,10 +1215,14 @@ int knn_launch_warp(kp_ctx *ctx, KnnParams &p, int64_t grid_queries)
 template <int NB, int R>
 int knn_launch_hist(kp_ctx *ctx, KnnParams &p)
 {
-    p.cap = p.k + 12;
-    size_t smem = (size_t)HQ_THREADS * ((size_t)p.cap * sizeof(unsigned long long) + (size_t)NB * sizeof(unsigned short));
-    if (smem > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist<NB, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_hist<NB, R><<<kp_blocks(p.nq, HQ_THREADS), HQ_THREADS, smem, ctx->stream>>>(p);
+    // the per-thread buffer (k + slack entries of 8 bytes) is what limits occupancy for large k: smaller CTAs pack the
+    // 227 KB of an SM more tightly
+    constexpr int T = NB <= 32 ? 128 : 64;
+    static const int slack = getenv("KP_KNN_SLACK") ? atoi(getenv("KP_KNN_SLACK")) : 8;   // swept: 6 / 8 / 12
+    p.cap = p.k + slack;
+    size_t smem = (size_t)T * ((size_t)p.cap * sizeof(unsigned long long) + (size_t)NB * sizeof(unsigned short));
+    if (smem > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist<NB, R, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_hist<NB, R, T><<<kp_blocks(p.nq, T), T, smem, ctx->stream>>>(p);
     KP_LAUNCH_CHECK(ctx);
     return KP_OK;
 }

@@ -29,7 +29,7 @@ def child():
         ctx.check(ctx.lib.kp_sor_mask(ctx.handle, d.ptr, n, k, 2.0, hint, keep.ptr, None, None, C.byref(kept)))
     pr = ctx.profile_read()
     out = {kk: round(v["ms"] / 2, 3) for kk, v in pr.items() if kk.startswith("knn") or kk in ("sor_knn", "radix_sort", "grid_hash")}
-    print(json.dumps({"k": k, "base": mult, "rad": os.environ.get("KP_KNN_RAD"), "cm": os.environ.get("KP_KNN_COARSE_MULT"), "kept": kept.value, "n": n, "ms": out}))
+    print(json.dumps({"k": k, "base": mult, "slack": os.environ.get("KP_KNN_SLACK"), "kept": kept.value, "n": n, "ms": out}))
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
@@ -37,10 +37,8 @@ if __name__ == "__main__":
     else:
         cfgs = []
         for k in (20, 50):
-            for rad in (1,):
-                for base in (1.5,):
-                    for cm in (3,):
-                        cfgs.append(dict(SW_K=k, SW_BASE=base, KP_KNN_RAD=rad, KP_KNN_COARSE_MULT=cm))
+            for slack in (8,):
+                cfgs.append(dict(SW_K=k, SW_BASE=1.5, KP_KNN_SLACK=slack))
         for c in cfgs:
             env = dict(os.environ, KP_DEBUG_KNN="1", **{a: str(b) for a, b in c.items()})
             r = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
