@@ -18,7 +18,10 @@
 #include "kp_umeyama.cuh"
 
 namespace {
-constexpr int ICP_THREADS = 256;
+#ifndef ICP_THREADS_N
+#define ICP_THREADS_N 256
+#endif
+constexpr int ICP_THREADS = ICP_THREADS_N;
 #ifndef ICP_MIN_CTAS
 #define ICP_MIN_CTAS 4
 #endif
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __
     if (tid == 0) s_ticket = atomicAdd(&st->ticket, 1u);
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
-    // ---- last CTA: deterministic cross-CTA sum.  Warp w adds slots w, w+8, ... in order, eight loads in
+    // ---- last CTA: deterministic cross-CTA sum.  Warp w adds slots w, w+8, ... in order, 24 loads in
     // flight at a time; then the 8 partial sums in order.
     __threadfence();
     {
@@ -346,6 +349,13 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __
         if (lane < ICP_NV) {
             constexpr int W = ICP_THREADS / 32;
             unsigned b = warp;
+            for (; b + 23 * W < gridDim.x; b += 24 * W) {
+                double t[24];
+#pragma unroll
+                for (int u = 0; u < 24; ++u) t[u] = __ldcg(p.slots + (size_t)(b + u * W) * ICP_NV + lane);
+#pragma unroll
+                for (int u = 0; u < 24; ++u) s += t[u];
+            }
             for (; b + 7 * W < gridDim.x; b += 8 * W) {
                 double t[8];
 #pragma unroll
