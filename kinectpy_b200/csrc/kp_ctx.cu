@@ -45,6 +45,9 @@ int kp_ctx_create(int device, kp_ctx **out)
     KP_CUDA(ctx, cudaMallocHost((void **)&ctx->h_scratch, ctx->scratch_bytes));
     KP_CUDA(ctx, cudaMalloc((void **)&ctx->d_scratch, ctx->scratch_bytes));
     KP_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, ctx->scratch_bytes, ctx->stream));
+    KP_CUDA(ctx, cudaMalloc((void **)&ctx->d_lb_state, sizeof(unsigned long long) * kp_ctx::LB_TILES + 256));
+    KP_CUDA(ctx, cudaMemsetAsync(ctx->d_lb_state, 0, sizeof(unsigned long long) * kp_ctx::LB_TILES + 256, ctx->stream));
+    ctx->d_lb_ticket = (unsigned int *)(ctx->d_lb_state + kp_ctx::LB_TILES);
     KP_CUDA(ctx, cudaEventCreate(&ctx->t0));
     KP_CUDA(ctx, cudaEventCreate(&ctx->t1));
     cudaDeviceProp prop;
@@ -65,6 +68,7 @@ int kp_ctx_destroy(kp_ctx *ctx)
     if (ctx->l2_flush) cudaFree(ctx->l2_flush);
     cudaFreeHost(ctx->h_scratch);
     cudaFree(ctx->d_scratch);
+    if (ctx->d_lb_state) cudaFree(ctx->d_lb_state);
     cudaEventDestroy(ctx->t0);
     cudaEventDestroy(ctx->t1);
     cudaStreamDestroy(ctx->stream);

@@ -9,7 +9,8 @@
 // normal-equation scalars in double, reduced with warp shuffles (xor butterfly), then a fixed-order
 // sum over the warps of the CTA, then per-CTA slots; (iv) the last CTA to finish (integer ticket)
 // adds the slots in a fixed order, evaluates fitness / rmse / the convergence test, solves the 6x6
-// system, composes T and publishes the next update and a `done` flag.  The host enqueues
+// system cooperatively (one thread per matrix element, the operations of the scalar elimination in the
+// same order), composes T and publishes the next update, the pass counter and a `done` flag.  The host enqueues
 // max_iter+1 passes without reading anything back; passes after `done` return immediately.
 #include <math.h>
 #include <string.h>
@@ -36,7 +37,7 @@ struct IcpState {
     long long ncorr;
     int done, iters;
     unsigned int ticket;
-    int pad;
+    int pass;                   // number of the pass the next launch executes (advanced by the last CTA)
 };
 
 struct IcpParams {
@@ -52,7 +53,7 @@ struct IcpParams {
     int ns;
     double r2;
     double slack;               // bound on (fp32 d2) - d2 for d2 <= max_corr^2, points near the grid
-    int pass, max_iter;
+    int max_iter;
     double rel_fit, rel_rmse;
     IcpState *st;
     double *slots;              // [gridDim.x][ICP_NV]
@@ -71,28 +72,45 @@ __global__ void __launch_bounds__(256) k_icp_init(const float *src, int ns, cons
     out[3 * (int64_t)i + 2] = kp_affine(T[8], T[9], T[10], T[11], X, Y, Z);
 }
 
-__device__ bool icp_solve6(double M[6][7], double *x)
+// 6x6 solve by Gaussian elimination with partial pivoting on the augmented matrix M[6][7] in shared memory,
+// executed by the whole (last) CTA: thread (r, j) = tid / 7, tid % 7 owns one element.  Every step performs
+// exactly the operations of the scalar loop nest (f = M[r][c] / M[c][c]; M[r][j] -= f * M[c][j] for j >= c),
+// element-parallel, so the result is the one a single thread would get, without its serial latency chain.
+// Returns (to every thread) whether the system was solvable; x[] is valid then.
+__device__ bool icp_solve6_cta(double (*M)[7], double *x, int tid)
 {
+    const int r = tid / 7, j = tid % 7;
+    const bool own = tid < 42;
+    bool ok = true;
     for (int c = 0; c < 6; ++c) {
         int pv = c;
         double best = fabs(M[c][c]);
-        for (int r = c + 1; r < 6; ++r)
-            if (fabs(M[r][c]) > best) { best = fabs(M[r][c]); pv = r; }
-        if (!(best > 1e-300)) return false;
-        if (pv != c)
-            for (int j = 0; j < 7; ++j) { double t = M[c][j]; M[c][j] = M[pv][j]; M[pv][j] = t; }
-        for (int r = c + 1; r < 6; ++r) {
-            double f = M[r][c] / M[c][c];
-            for (int j = c; j < 7; ++j) M[r][j] -= f * M[c][j];
+        for (int rr = c + 1; rr < 6; ++rr) {
+            const double v = fabs(M[rr][c]);
+            if (v > best) { best = v; pv = rr; }
+        }
+        if (!(best > 1e-300)) { ok = false; break; }          // uniform: every thread read the same column
+        __syncthreads();
+        if (own && r == c && pv != c) { const double t = M[c][j]; M[c][j] = M[pv][j]; M[pv][j] = t; }
+        __syncthreads();
+        double nv = 0.0;
+        const bool upd = own && r > c && j >= c;
+        if (upd) { const double f = M[r][c] / M[c][c]; nv = M[r][j] - f * M[c][j]; }
+        __syncthreads();
+        if (upd) M[r][j] = nv;
+        __syncthreads();
+    }
+    if (ok && tid == 0) {
+        for (int rr = 5; rr >= 0; --rr) {
+            double sacc = M[rr][6];
+            for (int jj = rr + 1; jj < 6; ++jj) sacc -= M[rr][jj] * x[jj];
+            x[rr] = sacc / M[rr][rr];
         }
     }
-    for (int r = 5; r >= 0; --r) {
-        double s = M[r][6];
-        for (int j = r + 1; j < 6; ++j) s -= M[r][j] * x[j];
-        x[r] = s / M[r][r];
-        if (!isfinite(x[r])) return false;
-    }
-    return true;
+    __syncthreads();
+    if (ok)
+        for (int rr = 0; rr < 6; ++rr) if (!isfinite(x[rr])) ok = false;
+    return ok;
 }
 
 // nearest target point inside max_corr (position in g.pts, -1 = none); `prev` = last pass's partner or -1.
@@ -176,50 +194,62 @@ __device__ __forceinline__ int icp_nearest(const KpGridDev &g, double sx, double
     return bpos;
 }
 
-// last CTA, one thread: fitness / rmse / convergence test, 6x6 solve, next update (kept out of line so its
-// registers do not count against the per-point part of the kernel)
-__device__ __noinline__ void icp_finish(const IcpParams &p, IcpState *st, const double *tot)
+// last CTA, all threads: fitness / rmse / convergence test, 6x6 solve, next update
+__device__ void icp_finish(const IcpParams &p, IcpState *st, const double *tot, int pass, int tid)
 {
+    __shared__ double M[6][7];
+    __shared__ double x[6];
+    __shared__ double Un[16];
+    __shared__ int s_done;
     const double nc = tot[28];
-    const double fit = p.ns > 0 ? nc / (double)p.ns : 0.0;
-    const double rmse = nc > 0 ? sqrt(tot[27] / nc) : 0.0;
-    const double pfit = st->fitness, prmse = st->rmse;
-    st->fitness = fit; st->rmse = rmse; st->ncorr = (long long)nc;
-    st->ticket = 0;
-    bool done = false;
-    if (p.pass > 0) {
-        st->iters = p.pass;
-        if (fabs(pfit - fit) < p.rel_fit && fabs(prmse - rmse) < p.rel_rmse) done = true;
-    }
-    if (p.pass == p.max_iter) done = true;
-    if (done) { st->done = 1; return; }
-    double Un[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    if (p.mode == ICP_POINT) {
-        if (nc > 0) kp_umeyama(tot, nc, Un);
-    } else {
-        double M[6][7];
-        {
-            int k = 0;
-            for (int a = 0; a < 6; ++a)
-                for (int b = a; b < 6; ++b) { M[a][b] = tot[k]; M[b][a] = tot[k]; ++k; }
-            for (int a = 0; a < 6; ++a) M[a][6] = -tot[21 + a];
+    if (tid == 0) {
+        const double fit = p.ns > 0 ? nc / (double)p.ns : 0.0;
+        const double rmse = nc > 0 ? sqrt(tot[27] / nc) : 0.0;
+        const double pfit = st->fitness, prmse = st->rmse;
+        st->fitness = fit; st->rmse = rmse; st->ncorr = (long long)nc;
+        st->ticket = 0;
+        st->pass = pass + 1;
+        bool done = false;
+        if (pass > 0) {
+            st->iters = pass;
+            if (fabs(pfit - fit) < p.rel_fit && fabs(prmse - rmse) < p.rel_rmse) done = true;
         }
-        double x[6];
-        if (nc > 0 && icp_solve6(M, x)) {
+        if (pass >= p.max_iter) done = true;
+        if (done) st->done = 1;
+        s_done = done ? 1 : 0;
+    }
+    if (tid < 16) Un[tid] = (tid % 5 == 0) ? 1.0 : 0.0;
+    if (tid < 6) x[tid] = 0.0;
+    __syncthreads();
+    if (s_done) return;
+    if (p.mode == ICP_POINT) {
+        if (tid == 0 && nc > 0) kp_umeyama(tot, nc, Un);
+    } else {
+        if (tid < 42) {
+            const int r = tid / 7, j = tid % 7;
+            if (j == 6) M[r][6] = -tot[21 + r];
+            else {
+                const int a = r < j ? r : j, b = r < j ? j : r;
+                M[r][j] = tot[a * 6 - (a * (a - 1)) / 2 + (b - a)];   // packed upper triangle, row-major
+            }
+        }
+        __syncthreads();
+        const bool ok = icp_solve6_cta(M, x, tid);
+        if (ok && nc > 0 && tid == 0) {
             double ca = cos(x[0]), sa = sin(x[0]), cb = cos(x[1]), sb = sin(x[1]), cg = cos(x[2]), sg = sin(x[2]);
             Un[0] = cg * cb; Un[1] = cg * sb * sa - sg * ca; Un[2] = cg * sb * ca + sg * sa; Un[3] = x[3];
             Un[4] = sg * cb; Un[5] = sg * sb * sa + cg * ca; Un[6] = sg * sb * ca - cg * sa; Un[7] = x[4];
             Un[8] = -sb;     Un[9] = cb * sa;                Un[10] = cb * ca;               Un[11] = x[5];
         }
     }
-    double Tn[16];
-    for (int i2 = 0; i2 < 4; ++i2)
-        for (int j = 0; j < 4; ++j) {
-            double s = 0;
-            for (int k = 0; k < 4; ++k) s = s + Un[4 * i2 + k] * st->T[4 * k + j];
-            Tn[4 * i2 + j] = s;
-        }
-    for (int i2 = 0; i2 < 16; ++i2) { st->T[i2] = Tn[i2]; st->U[i2] = Un[i2]; }
+    __syncthreads();
+    double tn = 0.0;
+    if (tid < 16) {
+        const int i2 = tid >> 2, j = tid & 3;
+        for (int k = 0; k < 4; ++k) tn = tn + Un[4 * i2 + k] * st->T[4 * k + j];
+    }
+    __syncthreads();                    // every T element has been read
+    if (tid < 16) { st->T[tid] = tn; st->U[tid] = Un[tid]; }
     __threadfence();
 }
 
@@ -234,6 +264,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __
     __shared__ unsigned int s_ticket;
     IcpState *st = p.st;
     if (st->done) return;
+    const int pass = st->pass;          // advanced only after every CTA has taken its ticket
     const KpGridDev &g = p.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = blockIdx.x * ICP_THREADS + tid;
@@ -245,7 +276,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __
     if (i < p.ns) {
         double sx = p.cur[3 * (int64_t)i], sy = p.cur[3 * (int64_t)i + 1], sz = p.cur[3 * (int64_t)i + 2];
         int prev = -1;
-        if (p.pass > 0) {
+        if (pass > 0) {
             const double *U = st->U;
             const double x2 = kp_affine(U[0], U[1], U[2], U[3], sx, sy, sz);
             const double y2 = kp_affine(U[4], U[5], U[6], U[7], sx, sy, sz);
@@ -374,7 +405,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __
         tot[tid] = s;
     }
     __syncthreads();
-    if (tid == 0) icp_finish(p, st, tot);
+    icp_finish(p, st, tot, pass, tid);
 }
 }  // namespace
 
@@ -492,7 +523,6 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
     IcpState init;
     memset(&init, 0, sizeof init);
     for (int i = 0; i < 16; ++i) { init.T[i] = h_init16[i]; init.U[i] = (i % 5 == 0) ? 1.0 : 0.0; }
-    p.pass = 0;
     {
         // moving source = init * src.  (Re-ordering the source by target-grid cell was measured: the voxel order the
         // source arrives in is already coherent, and the extra sort cost more than the lookups it saved.)
@@ -508,7 +538,6 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
         }
     }
     for (int pass = 0; pass <= max_iter; ++pass) {
-        p.pass = pass;
         if (p.mode == ICP_POINT) k_icp_iter<ICP_POINT><<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
         else if (p.mode == ICP_COLORED) k_icp_iter<ICP_COLORED><<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
         else k_icp_iter<ICP_PLANE><<<grid, ICP_THREADS, 0, ctx->stream>>>(p);

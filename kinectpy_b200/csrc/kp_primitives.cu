@@ -1,5 +1,5 @@
 // kp_primitives.cu -- device-wide building blocks written for this library:
-// ordered stream compaction (ballot scan), stable LSD radix sort of (key, index) pairs,
+// single-pass ordered stream compaction (ballot scan + decoupled look-back), stable LSD radix sort of (key, index) pairs,
 // run-head extraction, bounds, canonical double sums.  No CUB/Thrust on the product path.
 #include <math.h>
 #include "kp_common.cuh"
@@ -131,6 +131,111 @@ __global__ void __launch_bounds__(SC_THREADS) k_flag_scatter(int64_t n, Flag fla
     }
 }
 
+// ---- decoupled look-back (single-pass scan): tile t publishes its aggregate, then walks back over its
+// predecessors' words (32 at a time, one per lane) until it meets an inclusive prefix.  A word carries
+// {epoch:30, flag:2, value:32}; words of earlier calls have another epoch and read as "not ready", so the state
+// array is never cleared.  Tiles are numbered by an atomic ticket, so every predecessor of a running tile has
+// started (forward progress does not depend on the order the hardware schedules CTAs in).
+constexpr unsigned LB_AGG = 1u, LB_INCL = 2u;
+__device__ __forceinline__ unsigned long long lb_pack(unsigned epoch, unsigned flag, unsigned v)
+{
+    return ((unsigned long long)((epoch << 2) | flag) << 32) | v;
+}
+// executed by one full warp; returns the exclusive prefix of `tile` to every lane
+__device__ __forceinline__ unsigned lb_exclusive(volatile unsigned long long *state, unsigned tile, unsigned agg,
+                                                 unsigned epoch, int lane)
+{
+    if (tile == 0) {
+        if (lane == 0) state[0] = lb_pack(epoch, LB_INCL, agg);
+        return 0u;
+    }
+    if (lane == 0) state[tile] = lb_pack(epoch, LB_AGG, agg);
+    unsigned excl = 0;
+    int pos = (int)tile - 1;
+    for (;;) {
+        const int idx = pos - lane;
+        unsigned flag = LB_INCL, val = 0;           // lanes that ran off the front: an inclusive prefix of 0
+        if (idx >= 0) {
+            unsigned long long w;
+            do { w = state[idx]; } while ((unsigned)(w >> 34) != epoch);
+            flag = (unsigned)(w >> 32) & 3u;
+            val = (unsigned)w;
+        }
+        const unsigned incl_mask = __ballot_sync(KP_FULL, flag == LB_INCL);
+        const int first = __ffs(incl_mask) - 1;     // nearest predecessor holding an inclusive prefix
+        const unsigned take = first < 0 ? KP_FULL : ((2u << first) - 1u);
+        unsigned v = ((take >> lane) & 1u) ? val : 0u;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(KP_FULL, v, s);
+        excl += v;
+        if (first >= 0) break;
+        pos -= 32;
+    }
+    if (lane == 0) state[tile] = lb_pack(epoch, LB_INCL, excl + agg);
+    return excl;
+}
+
+template <class Flag, class Emit>
+__global__ void __launch_bounds__(SC_THREADS) k_flag_compact(int64_t n, Flag flag, Emit emit, unsigned long long *state,
+                                                             unsigned int *ticket, unsigned epoch, int32_t *total)
+{
+    __shared__ int cnt[SC_ITEMS * (SC_THREADS / 32)];
+    __shared__ unsigned s_tile;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) *ticket = 0;        // the last ticket of this launch re-arms the counter
+        s_tile = t;
+    }
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const int64_t base = (int64_t)tile * SC_TILE;
+    bool f[SC_ITEMS];
+    int rank[SC_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j) {
+        int64_t i = base + j * SC_THREADS + threadIdx.x;
+        f[j] = i < n && flag(i);
+        unsigned b = __ballot_sync(KP_FULL, f[j]);
+        rank[j] = __popc(b & ((1u << lane) - 1u));
+        if (lane == 0) cnt[j * (SC_THREADS / 32) + w] = __popc(b);
+    }
+    __syncthreads();
+    if (w == 0) {
+        // element order inside the tile is (j, warp, lane) = entry order of cnt[]; a lane owns two entries
+        const int c0 = cnt[2 * lane], c1 = cnt[2 * lane + 1];
+        const int s = c0 + c1;
+        int incl = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(KP_FULL, incl, d);
+            if (lane >= d) incl += y;
+        }
+        const unsigned agg = (unsigned)__shfl_sync(KP_FULL, incl, 31);
+        const unsigned excl = lb_exclusive(state, tile, agg, epoch, lane);
+        cnt[2 * lane] = (int)excl + incl - s;
+        cnt[2 * lane + 1] = (int)excl + incl - s + c0;
+        if (tile == gridDim.x - 1 && lane == 0) *total = (int32_t)(excl + agg);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j) {
+        int64_t i = base + j * SC_THREADS + threadIdx.x;
+        if (i < n) emit(i, f[j], cnt[j * (SC_THREADS / 32) + w] + rank[j]);
+    }
+}
+
+// next look-back epoch of the context (0 is never valid: the state starts zeroed)
+int lb_next_epoch(kp_ctx *ctx, unsigned *epoch)
+{
+    if (++ctx->lb_epoch >= (1u << 30)) {
+        KP_CUDA(ctx, cudaMemsetAsync(ctx->d_lb_state, 0, sizeof(unsigned long long) * kp_ctx::LB_TILES, ctx->stream));
+        ctx->lb_epoch = 1;
+    }
+    *epoch = ctx->lb_epoch;
+    return KP_OK;
+}
+
 template <class Flag, class Emit>
 int compact_generic(kp_ctx *ctx, int64_t n, Flag flag, Emit emit, int32_t *d_total)
 {
@@ -139,6 +244,14 @@ int compact_generic(kp_ctx *ctx, int64_t n, Flag flag, Emit emit, int32_t *d_tot
         return KP_OK;
     }
     unsigned nb = kp_blocks(n, SC_TILE);
+    if (nb <= (unsigned)kp_ctx::LB_TILES) {
+        unsigned epoch;
+        KP_TRY(lb_next_epoch(ctx, &epoch));
+        k_flag_compact<<<nb, SC_THREADS, 0, ctx->stream>>>(n, flag, emit, ctx->d_lb_state, ctx->d_lb_ticket, epoch, d_total);
+        KP_LAUNCH_CHECK(ctx);
+        return KP_OK;
+    }
+    // more tiles than look-back words: count / scan / scatter
     int32_t *d_sums;
     KP_TRY(kp_ws(ctx, nb, &d_sums));
     k_flag_count<<<nb, SC_THREADS, 0, ctx->stream>>>(n, flag, d_sums);
