@@ -800,11 +800,20 @@ __global__ void __launch_bounds__(HQT) k_knn_hist(const __grid_constant__ KnnPar
     // HQ_U candidates per trip: the loads and the distance chains are independent, so one L1 round trip covers all of them
     constexpr int HQ_U = 4;   // swept: 8 is slower (columns hold 10-40 candidates; longer trips waste on the tail)
     auto count = [&](const int2 rr) {
+        if (rr.x >= rr.y) return;
+        // the next trip's loads are in flight while this one is binned
+        float4 nx[HQ_U];
+#pragma unroll
+        for (int u = 0; u < HQ_U; ++u) nx[u] = __ldg(g.pts + (rr.y - rr.x > u ? rr.x + u : rr.x));
         for (int t = rr.x; t < rr.y; t += HQ_U) {
             const int m = rr.y - t;
             float4 c[HQ_U];
 #pragma unroll
-            for (int u = 0; u < HQ_U; ++u) c[u] = __ldg(g.pts + (m > u ? t + u : t));
+            for (int u = 0; u < HQ_U; ++u) c[u] = nx[u];
+            if (m > HQ_U) {
+#pragma unroll
+                for (int u = 0; u < HQ_U; ++u) nx[u] = __ldg(g.pts + (m - HQ_U > u ? t + HQ_U + u : t + HQ_U));
+            }
             int bj[HQ_U];
 #pragma unroll
             for (int u = 0; u < HQ_U; ++u) bj[u] = hq_bin(hq_d32(me.x, me.y, me.z, c[u]), G.scale);
@@ -918,8 +927,10 @@ __global__ void __launch_bounds__(HQT) k_knn_hist(const __grid_constant__ KnnPar
     double sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int cnt = 0;
     bool bad = false, closed = false;
+    float4 cn = m > 0 ? __ldg(g.pts + (unsigned)buf[0]) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = 0; i < m; ++i) {
-        const float4 c = __ldg(g.pts + (unsigned)buf[i * HQT]);
+        const float4 c = cn;
+        if (i + 1 < m) cn = __ldg(g.pts + (unsigned)buf[(i + 1) * HQT]);     // next gather in flight during this evaluation
         const double d = kp_d2(qx, qy, qz, (double)c.x, (double)c.y, (double)c.z);
         const int id = __float_as_int(c.w);
         if (!hq_before(pd, pi, d, id)) bad = true;
