@@ -42,9 +42,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="WFOV", choices=["WFOV", "NFOV"])
-    ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--frames-per-step", type=int, default=0, help="frames per step and GPU (0 = 2 x streams)")
     ap.add_argument("--distinct-frames", type=int, default=4, help="synthetic frames rendered per rank (cycled)")
-    ap.add_argument("--streams", type=int, default=4, help="frames in flight per GPU")
+    ap.add_argument("--streams", type=int, default=0,
+                    help="frames in flight per GPU (0 = auto: 6 while every worker thread has a core to spin on, "
+                         "8 with sleeping waits when the box's ranks outnumber its cores)")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-resample", action="store_true", help="skip the config-C5 resampling leg")
@@ -140,13 +142,24 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # Host side of the frame pipeline: one worker thread per frame in flight.  A worker waits for its stream ~15
+    # times per frame; spinning waits are fastest while each worker has a core of its own, sleeping waits
+    # (measured: same throughput with 8 frames in flight instead of 6) when the ranks of the box outnumber its cores.
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(max(world, 1))))
+    if "KP_SYNC" not in os.environ:
+        os.environ["KP_SYNC"] = "block" if cores < local_world * 7 else "spin"
+    if args.streams <= 0:
+        args.streams = 8 if os.environ["KP_SYNC"] == "block" else 6
+    if args.frames_per_step <= 0:
+        args.frames_per_step = 2 * args.streams
     from kinectpy_b200.pipeline import PipelineConfig
     mode_px = {"WFOV": 1024 * 1024, "NFOV": 640 * 576}[args.mode]
     cfg = PipelineConfig(n_sensors=3, pixels=mode_px, n_streams=args.streams)
     workload = ("C4: 3 x %s synthetic depth frames -> unproject+transform+fuse -> voxel 1cm -> SOR(20,2.0) -> "
                 "floor removal (band 20cm, RANSAC 1cm x1000, SOR(50,0.30)) -> p2plane ICP x2 (max_corr 2cm, <=30 it)" % args.mode)
     config = {"workload": workload, "mode": args.mode, "sensors": 3, "frames_per_step_per_gpu": args.frames_per_step,
-              "distinct_frames": args.distinct_frames, "streams_per_gpu": args.streams, "sharding": "frames round-robin over ranks, no collective",
+              "distinct_frames": args.distinct_frames, "streams_per_gpu": args.streams, "host_wait": os.environ["KP_SYNC"], "host_cores": cores, "sharding": "frames round-robin over ranks, no collective",
               "l2": "flushed between timed steps (256 MiB memset on the timing stream)",
               "arithmetic": "decisions and sums in f64 on f32-stored points (no FMA contraction); fp32 only pre-selects candidates"}
 

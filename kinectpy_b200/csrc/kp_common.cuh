@@ -27,6 +27,7 @@ struct kp_ctx {
     size_t scratch_bytes = 1 << 16;
     std::string err;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaEvent_t ev_block = nullptr;   // blocking-sync event of kp_stream_wait
     int64_t launches = 0;
     void *l2_flush = nullptr;
     // profiling
@@ -73,6 +74,8 @@ static inline int kp_ws(kp_ctx *ctx, size_t count, T **out)
 }
 // copies `bytes` from device scratch (offset 0) to pinned host scratch and waits
 int kp_fetch_scratch(kp_ctx *ctx, size_t bytes);
+// waits for everything enqueued on the context's stream (spinning or sleeping, see kp_ctx.cu)
+int kp_stream_wait(kp_ctx *ctx);
 // every public entry point starts here: bind the device, recycle the workspace
 static inline void kp_enter(kp_ctx *ctx)
 {

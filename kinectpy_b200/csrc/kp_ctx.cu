@@ -1,7 +1,10 @@
 // kp_ctx.cu -- context, workspace, memory and timing entry points of the C ABI.
+#include <sched.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
+#include <thread>
 #include "kp_common.cuh"
 
 static thread_local std::string g_last_err;
@@ -69,6 +72,7 @@ int kp_ctx_destroy(kp_ctx *ctx)
     cudaFreeHost(ctx->h_scratch);
     cudaFree(ctx->d_scratch);
     if (ctx->d_lb_state) cudaFree(ctx->d_lb_state);
+    if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
     cudaEventDestroy(ctx->t0);
     cudaEventDestroy(ctx->t1);
     cudaStreamDestroy(ctx->stream);
@@ -247,7 +251,40 @@ int kp_ws_alloc(kp_ctx *ctx, size_t bytes, void **out)
 int kp_fetch_scratch(kp_ctx *ctx, size_t bytes)
 {
     KP_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    KP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return kp_stream_wait(ctx);
+}
+
+// How a host thread waits for its stream.  Spinning (cudaStreamSynchronize) has the lowest latency and is right
+// while every waiting thread has a core of its own; when the ranks of one box together run more worker threads
+// than there are cores (8 GPUs x 4 frames in flight on a small host), spinning threads steal the cores the
+// launching threads need, so the wait sleeps on a blocking event instead.  KP_SYNC=spin|block overrides;
+// auto = block iff cores < LOCAL_WORLD_SIZE x KP_WORKERS_HINT (the pipeline sets the hint to its worker count).
+static int kp_sync_blocking()
+{
+    static int mode = -1;
+    if (mode >= 0) return mode;
+    const char *e = getenv("KP_SYNC");
+    if (e && !strcmp(e, "block")) return mode = 1;
+    if (e && !strcmp(e, "spin")) return mode = 0;
+    long cores = 0;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) cores = CPU_COUNT(&set);
+    if (cores <= 0) cores = (long)std::thread::hardware_concurrency();
+    const char *lw = getenv("LOCAL_WORLD_SIZE");
+    const char *wh = getenv("KP_WORKERS_HINT");
+    const long ranks = lw ? atol(lw) : 1, workers = wh ? atol(wh) : 4;
+    return mode = (cores > 0 && cores < (ranks > 0 ? ranks : 1) * ((workers > 0 ? workers : 1) + 1)) ? 1 : 0;
+}
+
+int kp_stream_wait(kp_ctx *ctx)
+{
+    if (!kp_sync_blocking()) {
+        KP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return KP_OK;
+    }
+    if (!ctx->ev_block) KP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
+    KP_CUDA(ctx, cudaEventRecord(ctx->ev_block, ctx->stream));
+    KP_CUDA(ctx, cudaEventSynchronize(ctx->ev_block));
     return KP_OK;
 }
 

@@ -333,7 +333,7 @@ int kp_ransac_correspondence(kp_ctx *ctx, const float *d_src, int64_t n_src, con
     KP_CUDA(ctx, cudaMemcpyAsync(h_list.data(), list, sizeof(int32_t) * (size_t)nl, cudaMemcpyDeviceToHost, ctx->stream));
     KP_CUDA(ctx, cudaMemcpyAsync(h_good.data(), good, sizeof(int32_t) * (size_t)nl, cudaMemcpyDeviceToHost, ctx->stream));
     KP_CUDA(ctx, cudaMemcpyAsync(h_err.data(), err2, sizeof(double) * (size_t)nl, cudaMemcpyDeviceToHost, ctx->stream));
-    KP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KP_TRY(kp_stream_wait(ctx));
     // upstream's sequential rule over the hypotheses in order: better = higher fitness, then lower rmse;
     // every improvement tightens the exit iteration ceil(log(1 - confidence) / log(1 - fitness^ransac_n))
     double best_fit = 0.0, best_rmse = 0.0;

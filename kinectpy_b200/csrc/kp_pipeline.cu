@@ -162,8 +162,7 @@ int run_frame(kp_pipeline *pl, KpWorker &w, const uint16_t *depth_f, bool on_dev
         }
         kp_ws_reset(ctx);
     }
-    KP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return KP_OK;
+    return kp_stream_wait(ctx);
 }
 }  // namespace
 
@@ -179,6 +178,11 @@ int kp_pipeline_create(int device, const kp_pipeline_cfg *cfg, const float *h_xy
     p->cfg = *cfg;
     p->device = device;
     int nw = cfg->n_streams < 1 ? 1 : (cfg->n_streams > 16 ? 16 : cfg->n_streams);
+    {
+        char hint[16];
+        snprintf(hint, sizeof hint, "%d", nw);
+        setenv("KP_WORKERS_HINT", hint, 0);     // lets kp_stream_wait pick spin or sleep for this box (kp_ctx.cu)
+    }
     p->workers.resize(nw);
     const int S = cfg->S;
     const size_t NP = (size_t)S * cfg->P;

@@ -257,7 +257,7 @@ int kp_ransac_device(kp_ctx *ctx, const float *d_xyz, int64_t n, double thr, int
     KP_CUDA(ctx, cudaMemcpyAsync(h_planes.data(), planes, sizeof(double4) * iters, cudaMemcpyDeviceToHost, ctx->stream));
     KP_CUDA(ctx, cudaMemcpyAsync(h_valid.data(), pvalid, (size_t)iters, cudaMemcpyDeviceToHost, ctx->stream));
     if (d_counts) KP_CUDA(ctx, cudaMemcpyAsync(d_counts, cnt, sizeof(int64_t) * iters, cudaMemcpyDeviceToDevice, ctx->stream));
-    KP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KP_TRY(kp_stream_wait(ctx));
 
     // sum of squared inlier distances, needed only when two hypotheses tie on the inlier count
     std::vector<double> sq(iters, -1.0);
@@ -267,7 +267,7 @@ int kp_ransac_device(kp_ctx *ctx, const float *d_xyz, int64_t n, double thr, int
         KP_LAUNCH_CHECK(ctx);
         std::vector<double> hs((size_t)nblk * 2);
         KP_CUDA(ctx, cudaMemcpyAsync(hs.data(), slots, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost, ctx->stream));
-        KP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        KP_TRY(kp_stream_wait(ctx));
         double s = 0;
         for (int b = 0; b < nblk; ++b) s += hs[2 * b + 1];
         sq[h] = s;
@@ -315,7 +315,7 @@ int kp_ransac_device(kp_ctx *ctx, const float *d_xyz, int64_t n, double thr, int
     KP_LAUNCH_CHECK(ctx);
     std::vector<double> hs((size_t)nblk * 10);
     KP_CUDA(ctx, cudaMemcpyAsync(hs.data(), slots, sizeof(double) * nblk * 2, cudaMemcpyDeviceToHost, ctx->stream));
-    KP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KP_TRY(kp_stream_wait(ctx));
     double ninl = 0;
     for (int b = 0; b < nblk; ++b) ninl += hs[2 * b];
     if (h_ninliers) *h_ninliers = (int64_t)ninl;
@@ -325,14 +325,14 @@ int kp_ransac_device(kp_ctx *ctx, const float *d_xyz, int64_t n, double thr, int
         k_masked_moments<<<nblk, 256, 0, ctx->stream>>>(d_xyz, mask, (int)n, 0.0, 0.0, 0.0, slots);
         KP_LAUNCH_CHECK(ctx);
         KP_CUDA(ctx, cudaMemcpyAsync(hs.data(), slots, sizeof(double) * nblk * 10, cudaMemcpyDeviceToHost, ctx->stream));
-        KP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        KP_TRY(kp_stream_wait(ctx));
         double c3[3] = {0, 0, 0};
         for (int b = 0; b < nblk; ++b) for (int c = 0; c < 3; ++c) c3[c] += hs[10 * b + c];
         for (int c = 0; c < 3; ++c) c3[c] /= ninl;
         k_masked_moments<<<nblk, 256, 0, ctx->stream>>>(d_xyz, mask, (int)n, c3[0], c3[1], c3[2], slots);
         KP_LAUNCH_CHECK(ctx);
         KP_CUDA(ctx, cudaMemcpyAsync(hs.data(), slots, sizeof(double) * nblk * 10, cudaMemcpyDeviceToHost, ctx->stream));
-        KP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        KP_TRY(kp_stream_wait(ctx));
         double m6[6] = {0, 0, 0, 0, 0, 0};
         for (int b = 0; b < nblk; ++b) for (int c = 0; c < 6; ++c) m6[c] += hs[10 * b + 3 + c];
         double rp[4];

@@ -275,7 +275,7 @@ int resample_select_batch(kp_ctx *ctx, const float *d_xyz, const int64_t *h_off,
     // one read for the whole batch: valid counts (the ValueError of np.random.choice) and list overflows (fallback)
     std::vector<RselState> hs((size_t)B);
     KP_CUDA(ctx, cudaMemcpyAsync(hs.data(), st, sizeof(RselState) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-    KP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KP_TRY(kp_stream_wait(ctx));
     for (int b = 0; b < B; ++b)
         if ((int64_t)hs[(size_t)b].nvalid < N)
             return kp_set_err(ctx, KP_E_ARG, "select_points_randomly: cloud %d has %u valid (non-NaN) points, fewer than the %lld requested",
