@@ -120,6 +120,9 @@ int kp_prim_csum(kp_ctx *ctx, const double *d_x, int64_t n, double *d_tmp, doubl
 int kp_prim_count_u8(kp_ctx *ctx, const uint8_t *d_mask, int64_t n, int32_t *d_total);
 
 // ------------------------------------------------------- K1 / K2 device --
+// internal flag of kp_unproject_device: d_bounds_enc is [B][S][8], one row per sensor (the frame pipeline needs the
+// bounds of the master cloud and of every raw sub cloud as well as the fused ones: all come out of K1)
+constexpr int KP_UP_BOUNDS_PER_SENSOR = 1 << 16;
 int kp_unproject_device(kp_ctx *ctx, const uint16_t *d_depth, const float *d_xytab, const double *h_T, int B, int S,
                         int64_t P, int flags, double scale, float *d_xyz, uint8_t *d_valid, int16_t *d_xyz16,
                         int32_t *d_bounds_enc);

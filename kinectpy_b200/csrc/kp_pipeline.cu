@@ -45,7 +45,7 @@ namespace {
 
 int compact_rows(kp_ctx *ctx, KpWorker &w, int64_t n, const uint8_t *mask, int invert, const float *in, float *out)
 {
-    int32_t *d_total = (int32_t *)ctx->d_scratch + 32;
+    int32_t *d_total = (int32_t *)ctx->d_scratch + 128;     // clear of the K1 bounds rows fetched through the same scratch
     KP_TRY(kp_prim_compact_mask(ctx, n, mask, invert, in, w.pos, nullptr, d_total));
     return kp_prim_gather3(ctx, n, w.pos, in, out);
 }
@@ -64,23 +64,35 @@ int run_frame(kp_pipeline *pl, KpWorker &w, const uint16_t *depth_f, bool on_dev
         KP_CUDA(ctx, cudaMemcpyAsync(w.d_depth, depth_f, sizeof(uint16_t) * (size_t)NP, cudaMemcpyHostToDevice, ctx->stream));
         d_depth = w.d_depth;
     }
-    // ---- K1: fused cloud in the master frame (+ raw sub clouds for ICP)
-    KP_TRY(kp_unproject_device(ctx, d_depth, pl->d_tab, pl->T_fuse.data(), 1, S, P, c.unproject_flags, c.scale, w.fused,
-                               nullptr, nullptr, w.enc));
-    if (c.do_icp && S > 1)
-        KP_TRY(kp_unproject_device(ctx, d_depth + P, pl->d_tab + 2 * P, nullptr, 1, S - 1, P, c.unproject_flags, c.scale,
-                                   w.raw, nullptr, nullptr, nullptr));
-    KP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, w.enc, 8 * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    KP_TRY(kp_fetch_scratch(ctx, 8 * sizeof(int32_t)));
-    float b6[6];
-    int64_t nvalid;
+    // ---- K1: fused cloud in the master frame (+ raw sub clouds for ICP); bounds and counts per sensor ride along
+    const bool icp = c.do_icp && S > 1;
+    const int nrows = S + (icp ? S - 1 : 0);
+    KP_TRY(kp_unproject_device(ctx, d_depth, pl->d_tab, pl->T_fuse.data(), 1, S, P, c.unproject_flags | KP_UP_BOUNDS_PER_SENSOR,
+                               c.scale, w.fused, nullptr, nullptr, w.enc));
+    if (icp)
+        KP_TRY(kp_unproject_device(ctx, d_depth + P, pl->d_tab + 2 * P, nullptr, 1, S - 1, P,
+                                   c.unproject_flags | KP_UP_BOUNDS_PER_SENSOR, c.scale, w.raw, nullptr, nullptr, w.enc + 8 * S));
+    KP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, w.enc, (size_t)nrows * 8 * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    KP_TRY(kp_fetch_scratch(ctx, (size_t)nrows * 8 * sizeof(int32_t)));
+    float sb6[2 * 6][6];          // per row: min xyz, max xyz
+    int64_t scount[2 * 6];
     {
         const int32_t *h = (const int32_t *)ctx->h_scratch;
-        for (int k = 0; k < 6; ++k) {
-            int32_t b = h[k] >= 0 ? h[k] : h[k] ^ 0x7fffffff;
-            memcpy(&b6[k], &b, 4);
+        for (int r = 0; r < nrows; ++r) {
+            for (int k = 0; k < 6; ++k) {
+                int32_t b = h[8 * r + k] >= 0 ? h[8 * r + k] : h[8 * r + k] ^ 0x7fffffff;
+                memcpy(&sb6[r][k], &b, 4);
+            }
+            scount[r] = h[8 * r + 6];
         }
-        nvalid = h[6];
+    }
+    float b6[6];
+    int64_t nvalid = 0;
+    for (int k = 0; k < 3; ++k) { b6[k] = INFINITY; b6[3 + k] = -INFINITY; }
+    for (int s = 0; s < S; ++s) {
+        nvalid += scount[s];
+        if (scount[s] <= 0) continue;
+        for (int k = 0; k < 3; ++k) { b6[k] = fminf(b6[k], sb6[s][k]); b6[3 + k] = fmaxf(b6[3 + k], sb6[s][3 + k]); }
     }
     res->n_fused = nvalid;
     // ---- filter_outliers: voxel + SOR
@@ -138,9 +150,8 @@ int run_frame(kp_pipeline *pl, KpWorker &w, const uint16_t *depth_f, bool on_dev
         KP_CUDA(ctx, cudaMemcpyAsync(h_out, cur, sizeof(float) * 3 * (size_t)ncur, cudaMemcpyDeviceToHost, ctx->stream));
     // ---- ICP refinement of every sub extrinsic: target = master cloud, source = sub cloud in its own frame
     if (c.do_icp && S > 1) {
-        float tb[6];
-        int64_t tn = 0, Mt = 0;
-        KP_TRY(kp_prim_bounds_fetch(ctx, w.fused, P, tb, &tn));
+        const float *tb = sb6[0];         // the master cloud is sensor 0 of the fused one
+        int64_t tn = scount[0], Mt = 0;
         KP_TRY(kp_voxel_device(ctx, w.fused, nullptr, nullptr, P, c.icp_voxel, tb, tn, w.A, nullptr, nullptr, nullptr, nullptr,
                                nullptr, &Mt));
         kp_ws_reset(ctx);
@@ -150,9 +161,8 @@ int run_frame(kp_pipeline *pl, KpWorker &w, const uint16_t *depth_f, bool on_dev
         KP_TRY(kp_grid_build(ctx, w.A, Mt, c.icp_max_corr * (1.0 + 1e-6), tb, &g));
         for (int s = 1; s < S && s <= 5; ++s) {
             const float *raw_s = w.raw + 3 * (size_t)(s - 1) * P;
-            float sb[6];
-            int64_t sn = 0, Ms = 0;
-            KP_TRY(kp_prim_bounds_fetch(ctx, raw_s, P, sb, &sn));
+            const float *sb = sb6[S + s - 1];
+            int64_t sn = scount[S + s - 1], Ms = 0;
             KP_TRY(kp_voxel_device(ctx, raw_s, nullptr, nullptr, P, c.icp_voxel, sb, sn, w.B, nullptr, nullptr, nullptr,
                                    nullptr, nullptr, &Ms));
             int64_t ncorr = 0;
@@ -218,7 +228,7 @@ int kp_pipeline_create(int device, const kp_pipeline_cfg *cfg, const float *h_xy
         if (cudaMalloc((void **)&w.mask, NP) != cudaSuccess) return fail("mask");
         if (cudaMalloc((void **)&w.mask2, NP) != cudaSuccess) return fail("mask");
         if (cudaMalloc((void **)&w.pos, sizeof(int32_t) * NP) != cudaSuccess) return fail("pos");
-        if (cudaMalloc((void **)&w.enc, sizeof(int32_t) * 8) != cudaSuccess) return fail("enc");
+        if (cudaMalloc((void **)&w.enc, sizeof(int32_t) * 8 * 16) != cudaSuccess) return fail("enc");
     }
     *out = p;
     return KP_OK;

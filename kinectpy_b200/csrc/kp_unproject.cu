@@ -20,7 +20,7 @@ struct UnprojParams {
     float *xyz;
     uint8_t *valid;
     int16_t *xyz16;
-    int32_t *bounds_enc;   // [B][8] ordered-int min xyz, max xyz, count, pad (nullable)
+    int32_t *bounds_enc;   // [B][8] (or [B][S][8] with KP_UP_BOUNDS_PER_SENSOR) ordered-int min xyz, max xyz, count, pad (nullable)
     double T[UP_MAX_S][12];
 };
 
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(UP_THREADS) k_unproject(const __grid_constant_
                     int u = red_i[tid][w];
                     v = tid < 3 ? min(v, u) : (tid < 6 ? max(v, u) : v + u);
                 }
-                int32_t *be = p.bounds_enc + 8 * b;
+                int32_t *be = p.bounds_enc + 8 * ((p.flags & KP_UP_BOUNDS_PER_SENSOR) ? (int64_t)b * p.S + s : (int64_t)b);
                 if (tid < 3) atomicMin(&be[tid], v);
                 else if (tid < 6) atomicMax(&be[tid], v);
                 else if (v) atomicAdd(&be[6], v);
@@ -309,7 +309,8 @@ int kp_unproject_device(kp_ctx *ctx, const uint16_t *d_depth, const float *d_xyt
     p.bounds_enc = d_bounds_enc;
     for (int s = 0; s < UP_MAX_S; ++s) fill_T12(h_T && s < S ? h_T + 16 * s : nullptr, p.T[s]);
     if (d_bounds_enc) {
-        k_bounds_init_batch<<<kp_blocks((int64_t)B * 8, 256), 256, 0, ctx->stream>>>(d_bounds_enc, B);
+        const int rows = (flags & KP_UP_BOUNDS_PER_SENSOR) ? B * S : B;
+        k_bounds_init_batch<<<kp_blocks((int64_t)rows * 8, 256), 256, 0, ctx->stream>>>(d_bounds_enc, rows);
         KP_LAUNCH_CHECK(ctx);
     }
     dim3 grid(kp_blocks(P, UP_TILE), (unsigned)S);

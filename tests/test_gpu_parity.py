@@ -114,6 +114,23 @@ def test_transform_bounds_compact(ctx, oracle):
         assert len(out) == m.sum()
 
 
+
+@pytest.mark.parametrize("n", [1, 31, 2047, 2048, 2049, 65536, 300007])
+def test_compact_single_pass_scan_across_tiles(ctx, n):
+    """Ordered compaction is one kernel: tiles of 2048 chained by a decoupled look-back whose per-tile words are
+    tagged with a per-call epoch (never cleared).  Ragged sizes around the tile edge, sparse / dense / run-structured
+    masks, and back-to-back calls on the same context (stale words of earlier calls must read as 'not ready')."""
+    rng = np.random.default_rng(n)
+    pts = rng.random((n, 3), dtype=np.float32)
+    masks = [(rng.random(n) < p).astype(np.uint8) for p in (0.001, 0.5, 0.999)]
+    masks.append(((np.arange(n) // 777) % 2).astype(np.uint8))      # long runs: whole tiles kept / dropped
+    for rep in range(2):
+        for m in masks:
+            for inv in (False, True):
+                sel = m.astype(bool) != inv
+                out, idx, _ = G.compact(ctx, pts, m, inv)
+                assert np.array_equal(idx, np.flatnonzero(sel)) and np.array_equal(out, pts[sel])
+
 # ------------------------------------------------------------------ K2 ----
 @pytest.mark.parametrize("n,voxel,scale", [(50000, 0.05, 1.0), (50000, 35.0, 1000.0), (3000, 0.01, 1.0), (17, 0.5, 1.0)])
 def test_voxel_downsample_bit_exact(ctx, oracle, n, voxel, scale):
