@@ -20,7 +20,7 @@ struct UnprojParams {
     float *xyz;
     uint8_t *valid;
     int16_t *xyz16;
-    int32_t *bounds_enc;   // [B][8] (or [B][S][8] with KP_UP_BOUNDS_PER_SENSOR) ordered-int min xyz, max xyz, count, pad (nullable)
+    int32_t *bounds_enc;   // BOUNDS variants: [B][S][tiles][warps][8] slots of ordered-int min xyz, max xyz, count, pad
     double T[UP_MAX_S][12];
 };
 
@@ -29,13 +29,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 // The CTA's slice of the calibration table is fetched once with a TMA bulk copy
 // (cp.async.bulk -> SASS UBLKCP) that completes on an mbarrier, kept stationary (registers) and
 // reused for every frame of the batch; depth streams through with one 128-bit load per thread.
-__global__ void __launch_bounds__(UP_THREADS) k_unproject(const __grid_constant__ UnprojParams p)
+// Compile-time variants (k4a int16 rounding, drop-any-zero rule, extrinsic, bounds) so a launch carries only its
+// own arithmetic: the flag tests and the dead branches they guard were a fifth of the instructions.
+template <bool INT16, bool DROP, bool HAS_T, bool BOUNDS>
+__global__ void __launch_bounds__(UP_THREADS, 3) k_unproject(const __grid_constant__ UnprojParams p)
 {
     __shared__ __align__(128) float2 tab_s[UP_TILE];
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ int red_i[7][UP_THREADS / 32];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int s = blockIdx.y;
     const int64_t p0 = (int64_t)blockIdx.x * UP_TILE;
     const int npx = (int)min((int64_t)UP_TILE, p.P - p0);
@@ -62,6 +63,16 @@ __global__ void __launch_bounds__(UP_THREADS) k_unproject(const __grid_constant_
 #pragma unroll
     for (int i = 0; i < 12; ++i) T[i] = p.T[s][i];
 
+    const int px0 = tid * UP_PPT;
+    const bool full = px0 + UP_PPT <= npx;
+    const bool vec_ok = (p.P % 8 == 0) && ((((uintptr_t)p.depth) & 15u) == 0u);
+    const bool vst_ok = (p.P % 4 == 0) && ((((uintptr_t)p.xyz) & 15u) == 0u);
+    // the first frame's depth word is requested before waiting for the table tile (two independent DRAM round
+    // trips overlap); after that the next frame's word is in flight while the current frame is computed and stored
+    const bool fast_ld = full && vec_ok;
+    uint4 vnext = make_uint4(0u, 0u, 0u, 0u);
+    if (fast_ld && p.B > 0) vnext = __ldg(reinterpret_cast<const uint4 *>(p.depth + ((int64_t)s * p.P + p0 + px0)));
+
     if (bulk) {
         uint32_t done = 0;
         while (!done) {
@@ -72,20 +83,16 @@ __global__ void __launch_bounds__(UP_THREADS) k_unproject(const __grid_constant_
         __syncthreads();
     }
 
-    const int px0 = tid * UP_PPT;
     float2 tb[UP_PPT];
 #pragma unroll
     for (int j = 0; j < UP_PPT; ++j) tb[j] = (px0 + j < npx) ? tab_s[px0 + j] : make_float2(NAN, NAN);
 
-    const bool full = px0 + UP_PPT <= npx;
-    const bool vec_ok = (p.P % 8 == 0) && ((((uintptr_t)p.depth) & 15u) == 0u);
-    const bool vst_ok = (p.P % 4 == 0) && ((((uintptr_t)p.xyz) & 15u) == 0u);
-
     for (int b = 0; b < p.B; ++b) {
         const int64_t row = ((int64_t)b * p.S + s) * p.P + p0 + px0;   // first pixel of this thread
         uint16_t dz[UP_PPT];
-        if (full && vec_ok) {
-            uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.depth + row));
+        if (fast_ld) {
+            const uint4 v = vnext;
+            if (b + 1 < p.B) vnext = __ldg(reinterpret_cast<const uint4 *>(p.depth + row + (int64_t)p.S * p.P));
             dz[0] = v.x & 0xffff; dz[1] = v.x >> 16; dz[2] = v.y & 0xffff; dz[3] = v.y >> 16;
             dz[4] = v.z & 0xffff; dz[5] = v.z >> 16; dz[6] = v.w & 0xffff; dz[7] = v.w >> 16;
         } else {
@@ -103,7 +110,7 @@ __global__ void __launch_bounds__(UP_THREADS) k_unproject(const __grid_constant_
             bool ok = !(isnan(xt) || isnan(yt)) && z != 0;
             double X, Y, Z;
             int16_t xi = 0, yi = 0, zi = 0;
-            if (p.flags & KP_UNPROJECT_INT16) {
+            if (INT16) {
                 const float zf = (float)z;
                 const float fx = __fmul_rn(xt, zf), fy = __fmul_rn(yt, zf);   // no FMA: k4a rounds the product first
                 if (ok) {
@@ -119,12 +126,12 @@ __global__ void __launch_bounds__(UP_THREADS) k_unproject(const __grid_constant_
                 Y = __dmul_rn(__dmul_rn((double)yt, (double)z), p.scale);
                 Z = __dmul_rn((double)z, p.scale);
             }
-            if (p.xyz16 && px0 + j < npx) {
+            if (INT16 && p.xyz16 && px0 + j < npx) {
                 int16_t *o = p.xyz16 + 3 * (row + j);
                 o[0] = xi; o[1] = yi; o[2] = zi;
             }
-            if ((p.flags & KP_UNPROJECT_DROP_ANY_ZERO) && (X == 0.0 || Y == 0.0 || Z == 0.0)) ok = false;
-            if (ok && p.has_T) {
+            if (DROP && (X == 0.0 || Y == 0.0 || Z == 0.0)) ok = false;
+            if (HAS_T && ok) {
                 const double x2 = kp_affine(T[0], T[1], T[2], T[3], X, Y, Z);
                 const double y2 = kp_affine(T[4], T[5], T[6], T[7], X, Y, Z);
                 const double z2 = kp_affine(T[8], T[9], T[10], T[11], X, Y, Z);
@@ -132,8 +139,8 @@ __global__ void __launch_bounds__(UP_THREADS) k_unproject(const __grid_constant_
             }
             float fx3 = ok ? (float)X : NAN, fy3 = ok ? (float)Y : NAN, fz3 = ok ? (float)Z : NAN;
             out[3 * j] = fx3; out[3 * j + 1] = fy3; out[3 * j + 2] = fz3;
-            if (ok) {
-                okmask |= 1u << j;
+            if (ok) okmask |= 1u << j;
+            if (BOUNDS && ok) {
                 ++cnt;
                 mn[0] = fminf(mn[0], fx3); mn[1] = fminf(mn[1], fy3); mn[2] = fminf(mn[2], fz3);
                 mx[0] = fmaxf(mx[0], fx3); mx[1] = fmaxf(mx[1], fy3); mx[2] = fmaxf(mx[2], fz3);
@@ -161,7 +168,10 @@ __global__ void __launch_bounds__(UP_THREADS) k_unproject(const __grid_constant_
                     if (px0 + j < npx) p.valid[row + j] = (okmask >> j) & 1u;
             }
         }
-        if (p.bounds_enc) {
+        if (BOUNDS) {
+            // warp shuffles, then lane 0 parks the warp's 7 numbers in its own 32-byte slot; a small kernel folds
+            // the slots of a frame afterwards.  No CTA barrier and no atomics inside the frame loop (thousands of
+            // warps hitting the frame's 7 words with atomics cost more than the whole unprojection).
             int enc[7] = {kp_f2ord(mn[0]), kp_f2ord(mn[1]), kp_f2ord(mn[2]), kp_f2ord(mx[0]), kp_f2ord(mx[1]), kp_f2ord(mx[2]), cnt};
 #pragma unroll
             for (int sft = 16; sft >= 1; sft >>= 1) {
@@ -172,34 +182,54 @@ __global__ void __launch_bounds__(UP_THREADS) k_unproject(const __grid_constant_
                 }
                 enc[6] += __shfl_xor_sync(KP_FULL, enc[6], sft);
             }
-            __syncthreads();   // previous frame's reader is done with red_i
             if (lane == 0) {
-#pragma unroll
-                for (int c = 0; c < 7; ++c) red_i[c][warp] = enc[c];
-            }
-            __syncthreads();
-            if (tid < 7) {
-                int v = red_i[tid][0];
-                for (int w = 1; w < UP_THREADS / 32; ++w) {
-                    int u = red_i[tid][w];
-                    v = tid < 3 ? min(v, u) : (tid < 6 ? max(v, u) : v + u);
-                }
-                int32_t *be = p.bounds_enc + 8 * ((p.flags & KP_UP_BOUNDS_PER_SENSOR) ? (int64_t)b * p.S + s : (int64_t)b);
-                if (tid < 3) atomicMin(&be[tid], v);
-                else if (tid < 6) atomicMax(&be[tid], v);
-                else if (v) atomicAdd(&be[6], v);
+                int4 *slot = reinterpret_cast<int4 *>(p.bounds_enc) +
+                             2 * ((((int64_t)b * p.S + s) * gridDim.x + blockIdx.x) * (UP_THREADS / 32) + (tid >> 5));
+                slot[0] = make_int4(enc[0], enc[1], enc[2], enc[3]);
+                slot[1] = make_int4(enc[4], enc[5], enc[6], 0);
             }
         }
     }
 }
 
-__global__ void k_bounds_init_batch(int32_t *enc, int B)
+// folds `per_row` consecutive slots {min xyz, max xyz, count, -} into one row of the same layout
+__global__ void __launch_bounds__(256) k_bounds_fold(const int32_t *slots, int64_t per_row, int32_t *rows)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * 8) return;
-    int c = i & 7;
-    enc[i] = c < 3 ? kp_f2ord(INFINITY) : (c < 6 ? kp_f2ord(-INFINITY) : 0);
+    __shared__ int red[7][8];
+    const int32_t *src = slots + (int64_t)blockIdx.x * per_row * 8;
+    int v[7] = {kp_f2ord(INFINITY), kp_f2ord(INFINITY), kp_f2ord(INFINITY), kp_f2ord(-INFINITY), kp_f2ord(-INFINITY),
+                kp_f2ord(-INFINITY), 0};
+    for (int64_t e = threadIdx.x; e < per_row; e += blockDim.x) {
+        const int4 a = reinterpret_cast<const int4 *>(src)[2 * e], c = reinterpret_cast<const int4 *>(src)[2 * e + 1];
+        v[0] = min(v[0], a.x); v[1] = min(v[1], a.y); v[2] = min(v[2], a.z);
+        v[3] = max(v[3], a.w); v[4] = max(v[4], c.x); v[5] = max(v[5], c.y);
+        v[6] += c.z;
+    }
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            v[c] = min(v[c], __shfl_xor_sync(KP_FULL, v[c], sft));
+            v[3 + c] = max(v[3 + c], __shfl_xor_sync(KP_FULL, v[3 + c], sft));
+        }
+        v[6] += __shfl_xor_sync(KP_FULL, v[6], sft);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) red[c][threadIdx.x >> 5] = v[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const int c = threadIdx.x;
+        int r = 0;
+        if (c < 7) {
+            r = red[c][0];
+            for (int w = 1; w < 8; ++w) r = c < 3 ? min(r, red[c][w]) : (c < 6 ? max(r, red[c][w]) : r + red[c][w]);
+        }
+        rows[8 * (int64_t)blockIdx.x + c] = r;
+    }
 }
+
 __global__ void k_bounds_decode_batch(const int32_t *enc, int B, float *bounds, int32_t *nvalid)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,16 +336,29 @@ int kp_unproject_device(kp_ctx *ctx, const uint16_t *d_depth, const float *d_xyt
     UnprojParams p;
     p.depth = d_depth; p.tab = (const float2 *)d_xytab; p.B = B; p.S = S; p.P = P; p.flags = flags;
     p.has_T = h_T != nullptr; p.scale = scale; p.xyz = d_xyz; p.valid = d_valid; p.xyz16 = d_xyz16;
-    p.bounds_enc = d_bounds_enc;
+    // bounds: the kernel leaves one slot per warp and frame, folded into d_bounds_enc's rows afterwards
+    const int64_t ntiles = kp_blocks(P, UP_TILE);
+    const int64_t nslots = (int64_t)B * S * ntiles * (UP_THREADS / 32);
+    int32_t *slots = nullptr;
+    if (d_bounds_enc) KP_TRY(kp_ws(ctx, (size_t)nslots * 8, &slots));
+    p.bounds_enc = slots;
     for (int s = 0; s < UP_MAX_S; ++s) fill_T12(h_T && s < S ? h_T + 16 * s : nullptr, p.T[s]);
+    dim3 grid(kp_blocks(P, UP_TILE), (unsigned)S);
+    const int variant = ((flags & KP_UNPROJECT_INT16) ? 1 : 0) | ((flags & KP_UNPROJECT_DROP_ANY_ZERO) ? 2 : 0) |
+                        (h_T ? 4 : 0) | (d_bounds_enc ? 8 : 0);
+#define KP_UP_CASE(v)                                                                                                 \
+    case v: k_unproject<((v) & 1) != 0, ((v) & 2) != 0, ((v) & 4) != 0, ((v) & 8) != 0><<<grid, UP_THREADS, 0, ctx->stream>>>(p); break;
+    switch (variant) {
+        KP_UP_CASE(0) KP_UP_CASE(1) KP_UP_CASE(2) KP_UP_CASE(3) KP_UP_CASE(4) KP_UP_CASE(5) KP_UP_CASE(6) KP_UP_CASE(7)
+        KP_UP_CASE(8) KP_UP_CASE(9) KP_UP_CASE(10) KP_UP_CASE(11) KP_UP_CASE(12) KP_UP_CASE(13) KP_UP_CASE(14) KP_UP_CASE(15)
+    }
+#undef KP_UP_CASE
+    KP_LAUNCH_CHECK(ctx);
     if (d_bounds_enc) {
         const int rows = (flags & KP_UP_BOUNDS_PER_SENSOR) ? B * S : B;
-        k_bounds_init_batch<<<kp_blocks((int64_t)rows * 8, 256), 256, 0, ctx->stream>>>(d_bounds_enc, rows);
+        k_bounds_fold<<<rows, 256, 0, ctx->stream>>>(slots, nslots / rows, d_bounds_enc);
         KP_LAUNCH_CHECK(ctx);
     }
-    dim3 grid(kp_blocks(P, UP_TILE), (unsigned)S);
-    k_unproject<<<grid, UP_THREADS, 0, ctx->stream>>>(p);
-    KP_LAUNCH_CHECK(ctx);
     return KP_OK;
 }
 
