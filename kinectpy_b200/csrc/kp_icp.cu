@@ -26,6 +26,7 @@ constexpr int ICP_THREADS = ICP_THREADS_N;
 #ifndef ICP_MIN_CTAS
 #define ICP_MIN_CTAS 4
 #endif
+constexpr int ICP_GROUP = 32;  // CTAs per group of the two-level hand-over at the end of a pass
 constexpr int ICP_NV = 29;   // 21 upper-triangular JtJ + 6 Jtr + sum d^2 + count
                              // (point-to-point: 3 sum s + 3 sum t + 9 sum t s^T in slots 0..14, same two tail slots)
 enum { ICP_PLANE = 0, ICP_POINT = 1, ICP_COLORED = 2 };
@@ -57,6 +58,8 @@ struct IcpParams {
     double rel_fit, rel_rmse;
     IcpState *st;
     double *slots;              // [gridDim.x][ICP_NV]
+    double *gslots;             // [groups][ICP_NV] group rows
+    unsigned int *gticket;      // [groups] zero between passes
 };
 
 __global__ void __launch_bounds__(256) k_icp_init(const float *src, int ns, const __grid_constant__ IcpParams p, IcpState init,
@@ -367,43 +370,53 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __
         for (int w = 0; w < ICP_THREADS / 32; ++w) s += sh[w][tid];
         p.slots[(size_t)blockIdx.x * ICP_NV + tid] = s;
     }
+    // ---- two-level hand-over.  CTAs form groups of ICP_GROUP consecutive blocks; the last CTA of a group to
+    // finish (group ticket) folds the group's slot rows into one group row, then takes the global ticket; the last
+    // group folds the group rows.  Each fold is one round of loads (a row per warp-slot, fixed order), instead of
+    // one CTA walking ~2000 rows; the tickets see ICP_GROUP and gridDim/ICP_GROUP atomics per address instead of
+    // gridDim.  Fixed tree -> the sums do not depend on which CTA does the folding.
+    constexpr int W = ICP_THREADS / 32;
+    const unsigned group = blockIdx.x / ICP_GROUP, ngroups = (gridDim.x + ICP_GROUP - 1) / ICP_GROUP;
+    const unsigned g0 = group * ICP_GROUP, gsize = min((unsigned)ICP_GROUP, gridDim.x - g0);
+    auto fold = [&](const double *rows, unsigned nrows, double *dst_sh) {
+        // warp w adds rows w, w + W, ... (all its loads in flight together), then the W partial sums in order
+        double sacc = 0;
+        if (lane < ICP_NV) {
+            unsigned r = warp;
+            for (; r + 3 * W < nrows; r += 4 * W) {
+                double t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) t[u] = __ldcg(rows + (size_t)(r + u * W) * ICP_NV + lane);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) sacc += t[u];
+            }
+            for (; r < nrows; r += W) sacc += __ldcg(rows + (size_t)r * ICP_NV + lane);
+        }
+        part[warp][lane] = sacc;
+        __syncthreads();
+        if (tid < ICP_NV) {
+            double t = 0;
+            for (int w = 0; w < W; ++w) t += part[w][tid];
+            dst_sh[tid] = t;
+        }
+        __syncthreads();
+    };
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&p.gticket[group], 1u);
+    __syncthreads();
+    if (s_ticket != gsize - 1) return;
+    __threadfence();
+    fold(p.slots + (size_t)g0 * ICP_NV, gsize, tot);
+    if (tid < ICP_NV) p.gslots[(size_t)group * ICP_NV + tid] = tot[tid];
+    if (tid == 0) p.gticket[group] = 0;             // re-armed for the next pass
     __threadfence();
     __syncthreads();
     if (tid == 0) s_ticket = atomicAdd(&st->ticket, 1u);
     __syncthreads();
-    if (s_ticket != gridDim.x - 1) return;
-    // ---- last CTA: deterministic cross-CTA sum.  Warp w adds slots w, w+8, ... in order, 24 loads in
-    // flight at a time; then the 8 partial sums in order.
+    if (s_ticket != ngroups - 1) return;
     __threadfence();
-    {
-        double s = 0;
-        if (lane < ICP_NV) {
-            constexpr int W = ICP_THREADS / 32;
-            unsigned b = warp;
-            for (; b + 23 * W < gridDim.x; b += 24 * W) {
-                double t[24];
-#pragma unroll
-                for (int u = 0; u < 24; ++u) t[u] = __ldcg(p.slots + (size_t)(b + u * W) * ICP_NV + lane);
-#pragma unroll
-                for (int u = 0; u < 24; ++u) s += t[u];
-            }
-            for (; b + 7 * W < gridDim.x; b += 8 * W) {
-                double t[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = __ldcg(p.slots + (size_t)(b + u * W) * ICP_NV + lane);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) s += t[u];
-            }
-            for (; b < gridDim.x; b += W) s += __ldcg(p.slots + (size_t)b * ICP_NV + lane);
-        }
-        part[warp][lane] = s;
-    }
-    __syncthreads();
-    if (tid < ICP_NV) {
-        double s = 0;
-        for (int w = 0; w < ICP_THREADS / 32; ++w) s += part[w][tid];
-        tot[tid] = s;
-    }
+    fold(p.gslots, ngroups, tot);
     __syncthreads();
     icp_finish(p, st, tot, pass, tid);
 }
@@ -519,6 +532,10 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
     KP_TRY(kp_ws(ctx, (size_t)(n_src > 0 ? n_src : 1) * 3, &p.cur));
     KP_TRY(kp_ws(ctx, (size_t)(n_src > 0 ? n_src : 1), &p.corr));
     KP_TRY(kp_ws(ctx, (size_t)grid * ICP_NV, &p.slots));
+    const int ngroups = (grid + ICP_GROUP - 1) / ICP_GROUP;
+    KP_TRY(kp_ws(ctx, (size_t)ngroups * ICP_NV, &p.gslots));
+    KP_TRY(kp_ws(ctx, (size_t)ngroups, &p.gticket));
+    KP_CUDA(ctx, cudaMemsetAsync(p.gticket, 0, sizeof(unsigned int) * (size_t)ngroups, ctx->stream));
     KP_TRY(kp_ws(ctx, 1, &p.st));
     IcpState init;
     memset(&init, 0, sizeof init);

@@ -564,7 +564,14 @@ __global__ void k_count_u8(const uint8_t *m, int64_t n, int32_t *total)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) c += m[i] != 0;
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) c += __shfl_xor_sync(KP_FULL, c, s);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
+    // one atomic per CTA (same-address atomics serialise at ~5 ns each: per warp they were the whole kernel)
+    __shared__ int wc[32];
+    if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) c += wc[w];
+        if (c) atomicAdd(total, c);
+    }
 }
 }  // namespace
 

@@ -181,7 +181,15 @@ __global__ void k_axis_max(const float *xyz, int64_t n, int axis, int32_t *enc)
     }
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) m = fmaxf(m, __shfl_xor_sync(KP_FULL, m, s));
-    if ((threadIdx.x & 31) == 0) atomicMax(enc, kp_f2ord(m));
+    // one atomic per CTA, and only if it would raise the word (same-address atomics serialise at ~5 ns each)
+    __shared__ float wm[32];
+    if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, wm[w]);
+        const int o = kp_f2ord(m);
+        if (o > *(volatile int32_t *)enc) atomicMax(enc, o);
+    }
 }
 __global__ void k_axis_max_init(int32_t *enc) { *enc = kp_f2ord(-INFINITY); }
 __global__ void k_band_mask(const float *xyz, int64_t n, int axis, double band, const int32_t *enc, uint8_t *lower)
