@@ -41,6 +41,7 @@ struct kp_ctx {
     unsigned int *d_lb_ticket = nullptr;
     unsigned int lb_epoch = 0;
     static constexpr int LB_TILES = 1 << 16;
+    int icp_passes_hint = 0;          // passes the last ICP on this context executed (sizes the next call's first batch)
 };
 
 int kp_set_err(kp_ctx *ctx, int code, const char *fmt, ...);

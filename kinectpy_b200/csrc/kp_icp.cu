@@ -554,15 +554,28 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
             p.src_int = si;
         }
     }
-    for (int pass = 0; pass <= max_iter; ++pass) {
-        if (p.mode == ICP_POINT) k_icp_iter<ICP_POINT><<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
-        else if (p.mode == ICP_COLORED) k_icp_iter<ICP_COLORED><<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
-        else k_icp_iter<ICP_PLANE><<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
-        KP_LAUNCH_CHECK(ctx);
-    }
-    KP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, p.st, sizeof(IcpState), cudaMemcpyDeviceToDevice, ctx->stream));
-    KP_TRY(kp_fetch_scratch(ctx, sizeof(IcpState)));
+    // Passes are identical launches (the pass number lives in the device state), enqueued without reading anything
+    // back; a pass launched after `done` returns at once but still costs a launch slot (~3.5 us).  So the first
+    // batch is sized from the previous call on this context (consecutive frames converge alike) and the state is
+    // fetched once after it; only a call that needs more passes than expected pays a second round trip.
     const IcpState *hs = (const IcpState *)ctx->h_scratch;
+    int launched = 0;
+    int batch = ctx->icp_passes_hint > 0 ? ctx->icp_passes_hint + 2 : 16;
+    for (;;) {
+        if (batch > max_iter + 1 - launched) batch = max_iter + 1 - launched;
+        for (int i = 0; i < batch; ++i) {
+            if (p.mode == ICP_POINT) k_icp_iter<ICP_POINT><<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
+            else if (p.mode == ICP_COLORED) k_icp_iter<ICP_COLORED><<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
+            else k_icp_iter<ICP_PLANE><<<grid, ICP_THREADS, 0, ctx->stream>>>(p);
+            KP_LAUNCH_CHECK(ctx);
+        }
+        launched += batch;
+        KP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, p.st, sizeof(IcpState), cudaMemcpyDeviceToDevice, ctx->stream));
+        KP_TRY(kp_fetch_scratch(ctx, sizeof(IcpState)));
+        if (hs->done || launched > max_iter) break;
+        batch = 6;
+    }
+    ctx->icp_passes_hint = hs->pass;        // passes executed
     // per executed pass: moving source read + write-back (48 B) and, per match, target point + normal (28 B)
     prof_scope__.add_bytes((double)(hs->iters + 1) * 76.0 * (double)n_src);
     if (h_T_out) memcpy(h_T_out, hs->T, sizeof(double) * 16);
