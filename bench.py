@@ -358,11 +358,11 @@ def main():
                         "calls": v["calls"], "algorithmic_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
         # the dominant KERNEL: profile scopes nest (sor_knn / normals / icp wrap their own launch groups), so the
         # roofline line is taken over the leaf families, each of which is one kernel (or one kernel per pass)
-        LEAF_KERNEL = {"knn_level0": "k_knn_hist", "knn_level1": "k_knn_whist", "knn_stragglers": "k_knn", "icp": "k_icp_iter",
+        LEAF_KERNEL = {"knn_level0": "k_knn_hist", "knn_level1": "k_knn_wbf", "knn_stragglers": "k_knn", "icp": "k_icp_iter",
                        "radix_sort": "k_rs_scatter", "ransac_score": "k_ransac_score", "unproject_transform": "k_unproject",
                        "voxel_mean": "k_voxel_mean", "voxel_keys": "k_voxel_keys", "grid_keys": "k_grid_keys",
-                       "grid_hash": "k_grid_insert", "compact_gather": "k_gather3", "compact_scan": "k_flag_scatter",
-                       "run_heads": "k_flag_scatter", "sor_stats": "k_csum_level", "bounds": "k_bounds"}
+                       "grid_hash": "k_grid_insert", "compact_gather": "k_gather3", "compact_scan": "k_flag_compact",
+                       "run_heads": "k_flag_compact", "sor_stats": "k_csum_level", "bounds": "k_bounds"}
         top = next((k for k in table if k in LEAF_KERNEL), None)
         roofline = None
         if top:
@@ -387,8 +387,8 @@ def main():
                         "avg_launch_ms": round(v["ms"] / n_launch, 4), "algorithmic_bytes_per_launch": round(v["bytes"] / n_launch),
                         "note": "dominant kernel by summed device time (CUDA events on the launching stream, one frame in flight). "
                                 "The neighbour search moves its compulsory bytes (cell-sorted float4 cloud in, one mean out) in a "
-                                "fraction of its run time: it is bound by instruction issue / latency (ncu: ~50 % issue-active, "
-                                "L1 hit rate 77-94 %, DRAM < 1 % busy), not by HBM; frac is reported against the HBM peak as the "
+                                "fraction of its run time: it is bound by instruction issue / latency (ncu: 48-59 % issue-active at 18-34 % occupancy, "
+                                "L1 hit rate 74-78 %, DRAM < 1 % busy), not by HBM; frac is reported against the HBM peak as the "
                                 "contract asks. HBM-bound kernels and their fractions are in `kernels`."}
         cb = None
         if world == 1 and not args.no_cpu_baseline:
