@@ -365,18 +365,25 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K *keys_in, con
     __syncthreads();
     const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * (RS_ITEMS * 32);
     K kreg[RS_ITEMS];
+    int32_t vreg[RS_ITEMS];
     int rank[RS_ITEMS];
     const unsigned lt = (1u << lane) - 1u;
+    // all of the thread's keys and values are requested before the first one is ranked: one memory round trip
+    // instead of one per item (the ranking below is a chain of warp votes that cannot start without its key)
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        const int64_t i = wbase + j * 32 + lane;
+        kreg[j] = 0; vreg[j] = 0;
+        if (i < n) { kreg[j] = keys_in[i]; vreg[j] = vals_in ? vals_in[i] : (int32_t)i; }
+    }
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
         int64_t i = wbase + j * 32 + lane;
         bool in = i < n;
         unsigned act = __ballot_sync(KP_FULL, in);
         rank[j] = 0;
-        kreg[j] = 0;
         if (in) {
-            K key = keys_in[i];
-            kreg[j] = key;
+            K key = kreg[j];
             unsigned d = (unsigned)(key >> shift) & 0xFFu;
             unsigned peers = __match_any_sync(act, d);
             int leader = __ffs(peers) - 1;
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K *keys_in, con
             unsigned d = (unsigned)(kreg[j] >> shift) & 0xFFu;
             int pos = cnt[w][d] + rank[j];
             keys_out[pos] = kreg[j];
-            vals_out[pos] = vals_in ? vals_in[i] : (int32_t)i;
+            vals_out[pos] = vreg[j];
         }
     }
 }
