@@ -867,11 +867,11 @@ __global__ void __launch_bounds__(HQT) k_knn_hist(const __grid_constant__ KnnPar
         int2 rng[9];
         const int order[9] = {4, 1, 3, 5, 7, 0, 2, 6, 8};
         const float fb = hq_budget(budget);
+        // the nine cell-map lookups are requested together, ahead of the first run's candidates
 #pragma unroll
-        for (int ci = 0; ci < 9; ++ci) {
-            rng[ci] = hq_column(g, G, order[ci] / 3 - 1, order[ci] % 3 - 1, 1, fb);
-            count(rng[ci]);
-        }
+        for (int ci = 0; ci < 9; ++ci) rng[ci] = hq_column(g, G, order[ci] / 3 - 1, order[ci] % 3 - 1, 1, fb);
+#pragma unroll
+        for (int ci = 0; ci < 9; ++ci) count(rng[ci]);
         select_bin();
         all = b < 0;                            // fewer than k in range: the loop ran over every bin, take them all
         if (b < 0) b = NB - 1;

@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __
     double J2[6] = {0, 0, 0, 0, 0, 0}, r2v = 0.0;
     if (i < p.ns) {
         double sx = p.cur[3 * (int64_t)i], sy = p.cur[3 * (int64_t)i + 1], sz = p.cur[3 * (int64_t)i + 2];
-        int prev = -1;
+        // last pass's partner is requested with the point itself (not after the update has been computed and stored)
+        int prev = pass > 0 ? p.corr[i] : -1;
         if (pass > 0) {
             const double *U = st->U;
             const double x2 = kp_affine(U[0], U[1], U[2], U[3], sx, sy, sz);
@@ -286,7 +287,6 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __
             const double z2 = kp_affine(U[8], U[9], U[10], U[11], sx, sy, sz);
             sx = x2; sy = y2; sz = z2;
             p.cur[3 * (int64_t)i] = sx; p.cur[3 * (int64_t)i + 1] = sy; p.cur[3 * (int64_t)i + 2] = sz;
-            prev = p.corr[i];
         }
         int bpos = -1;
         if (!isnan(sx) && g.dim[0] > 0) bpos = icp_nearest(g, sx, sy, sz, p.r2, p.slack, prev);
