@@ -118,6 +118,9 @@ int kp_prim_bounds(kp_ctx *ctx, const float *d_xyz, int64_t n, int32_t *d_bounds
 int kp_prim_bounds_fetch(kp_ctx *ctx, const float *d_xyz, int64_t n, float *h_bounds6, int64_t *h_nvalid);
 // canonical double sum (see DESIGN.md "canonical reductions"); result in d_out[0]; d_tmp >= ceil(n/1024)+ceil(n/1M)+2 doubles
 int kp_prim_csum(kp_ctx *ctx, const double *d_x, int64_t n, double *d_tmp, double *d_out);
+// the same tree over a transformed view: mode 1: max(x, 0); mode 2: x > 0 ? (x - *d_aux / aux_div)^2 : 0
+int kp_prim_csum_mode(kp_ctx *ctx, const double *d_x, int64_t n, double *d_tmp, double *d_out, int mode, const double *d_aux,
+                      double aux_div);
 int kp_prim_count_u8(kp_ctx *ctx, const uint8_t *d_mask, int64_t n, int32_t *d_total);
 
 // ------------------------------------------------------- K1 / K2 device --

@@ -1342,24 +1342,12 @@ int knn_launch(kp_ctx *ctx, KnnParams &p, const char *name, const float *d_xyz =
     }
 }
 
-// SOR statistics: the two canonical sums run on transformed copies of the mean array
-__global__ void k_sor_pos(const double *mean, int64_t n, double *out)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { double m = mean[i]; out[i] = m > 0 ? m : 0.0; }
-}
-__global__ void k_sor_sq(const double *mean, int64_t n, const double *sum, double valid, double *out, double *mu_out)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double mu = __ddiv_rn(*sum, valid);
-    if (i == 0) *mu_out = mu;
-    if (i < n) { double m = mean[i]; double d = __dsub_rn(m, mu); out[i] = m > 0 ? __dmul_rn(d, d) : 0.0; }
-}
-__global__ void k_sor_mask(const double *mean, int64_t n, const double *mu_p, const double *sq_p, double valid, double ratio,
+// SOR statistics: the two canonical sums run on transformed views of the mean array (kp_prim_csum_mode)
+__global__ void k_sor_mask(const double *mean, int64_t n, const double *sum_p, const double *sq_p, double valid, double ratio,
                            uint8_t *keep, double *stats)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double mu = *mu_p;
+    double mu = __ddiv_rn(*sum_p, valid);
     double sd = sqrt(__ddiv_rn(*sq_p, __dsub_rn(valid, 1.0)));
     double thr = __dadd_rn(mu, __dmul_rn(ratio, sd));
     if (i == 0) { stats[0] = mu; stats[1] = sd; stats[2] = thr; }
@@ -1405,9 +1393,8 @@ int kp_sor_device(kp_ctx *ctx, const float *d_xyz, int64_t n, int k, double rati
     if (!(cell > 0.0)) KP_TRY(kp_grid_auto_cell(ctx, d_xyz, n, h_bounds6, 0.5 * k > 4 ? 0.5 * k : 4, &cell));
     KpGrid g;
     KP_TRY(kp_grid_build_knn(ctx, d_xyz, n, cell, k, h_bounds6, &g));
-    double *mean = d_mean, *tmp, *red;
+    double *mean = d_mean, *red;
     if (!mean) KP_TRY(kp_ws(ctx, (size_t)n, &mean));
-    KP_TRY(kp_ws(ctx, (size_t)n, &tmp));
     KP_TRY(kp_ws(ctx, (size_t)n / 1024 + (size_t)n / 1048576 + 16, &red));
     {
         KnnParams p;
@@ -1417,19 +1404,15 @@ int kp_sor_device(kp_ctx *ctx, const float *d_xyz, int64_t n, int k, double rati
         p.cloud = nullptr; p.normals = nullptr; p.rcount = nullptr;
         KP_TRY(knn_launch(ctx, p, "sor_knn", d_xyz));
     }
-    KP_PROFB(ctx, "sor_stats", (double)n * (7.0 * 8.0 + 2.0));
+    KP_PROFB(ctx, "sor_stats", (double)n * (3.0 * 8.0 + 2.0));   // the mean array read by both sums and the mask pass, keep[] written and counted
     // NaN points never get a neighbour list: they count as "not computed" (mean = -1), like upstream's
     // empty-result branch; valid = number of points with a computed mean
-    double *d_sum = (double *)ctx->d_scratch, *d_mu = d_sum + 1, *d_sq = d_sum + 2, *d_stats = d_sum + 4;
+    double *d_sum = (double *)ctx->d_scratch, *d_sq = d_sum + 2, *d_stats = d_sum + 4;
     int32_t *d_cnt = (int32_t *)(d_sum + 8);
     unsigned nb = kp_blocks(n, 256);
-    k_sor_pos<<<nb, 256, 0, ctx->stream>>>(mean, n, tmp);
-    KP_LAUNCH_CHECK(ctx);
-    KP_TRY(kp_prim_csum(ctx, tmp, n, red, d_sum));
-    k_sor_sq<<<nb, 256, 0, ctx->stream>>>(mean, n, d_sum, (double)nvalid, tmp, d_mu);
-    KP_LAUNCH_CHECK(ctx);
-    KP_TRY(kp_prim_csum(ctx, tmp, n, red, d_sq));
-    k_sor_mask<<<nb, 256, 0, ctx->stream>>>(mean, n, d_mu, d_sq, (double)nvalid, ratio, d_keep, d_stats);
+    KP_TRY(kp_prim_csum_mode(ctx, mean, n, red, d_sum, 1, nullptr, 1.0));                 // sum of the positive means
+    KP_TRY(kp_prim_csum_mode(ctx, mean, n, red, d_sq, 2, d_sum, (double)nvalid));         // sum of (mean - mu)^2 over them
+    k_sor_mask<<<nb, 256, 0, ctx->stream>>>(mean, n, d_sum, d_sq, (double)nvalid, ratio, d_keep, d_stats);
     KP_LAUNCH_CHECK(ctx);
     KP_TRY(kp_prim_count_u8(ctx, d_keep, n, d_cnt));
     KP_TRY(kp_fetch_scratch(ctx, 10 * sizeof(double)));

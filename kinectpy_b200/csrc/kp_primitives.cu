@@ -549,21 +549,54 @@ int kp_prim_bounds_fetch(kp_ctx *ctx, const float *d_xyz, int64_t n, float *h_bo
 
 // ========================================================= canonical sum ==
 namespace {
-// one warp per group of 1024 values: lane t adds x[t], x[t+32], ... in order, then the butterfly
-__global__ void __launch_bounds__(256) k_csum_level(const double *x, int64_t n, double *out, int64_t groups)
+// one warp per group of 1024 values: lane t adds x[t], x[t+32], ... in order, then the butterfly.
+// mode selects what is summed (SOR statistics: the two sums run on transformed views of the mean array, so the
+// transform rides in the first level instead of a pass that writes a transformed copy):
+//   0: x[i]      1: x[i] > 0 ? x[i] : 0      2: x[i] > 0 ? (x[i] - mu)^2 : 0  with mu = *aux / aux_div
+__global__ void __launch_bounds__(256) k_csum_level(const double *x, int64_t n, double *out, int64_t groups, int mode,
+                                                    const double *aux, double aux_div)
 {
     int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= groups) return;
     const int lane = threadIdx.x & 31;
+    const double mu = mode == 2 ? __ddiv_rn(*aux, aux_div) : 0.0;
     int64_t lo = g * 1024;
     double acc = 0.0;
 #pragma unroll 4
     for (int r = 0; r < 32; ++r) {
         int64_t i = lo + r * 32 + lane;
-        if (i < n) acc = __dadd_rn(acc, x[i]);
+        if (i < n) {
+            double v = x[i];
+            if (mode == 1) v = v > 0 ? v : 0.0;
+            else if (mode == 2) { const double d = __dsub_rn(v, mu); v = v > 0 ? __dmul_rn(d, d) : 0.0; }
+            acc = __dadd_rn(acc, v);
+        }
     }
     acc = kp_butterfly_sum(acc);
     if (lane == 0) out[g] = acc;
+}
+// every further level in one CTA: cur[0..cn) -> groups of 1024 -> ... -> out[0]; scratch follows cur
+__global__ void __launch_bounds__(1024) k_csum_rest(double *cur, int64_t cn, double *out)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *nxt = cur + cn;
+    for (;;) {
+        const int64_t groups = (cn + 1023) / 1024;
+        double *dst = groups == 1 ? out : nxt;
+        for (int64_t g = warp; g < groups; g += 32) {
+            const int64_t lo = g * 1024;
+            double acc = 0.0;
+            for (int r = 0; r < 32; ++r) {
+                const int64_t i = lo + r * 32 + lane;
+                if (i < cn) acc = __dadd_rn(acc, cur[i]);
+            }
+            acc = kp_butterfly_sum(acc);
+            if (lane == 0) dst[g] = acc;
+        }
+        if (groups == 1) break;
+        __syncthreads();
+        cur = nxt; nxt = nxt + groups; cn = groups;
+    }
 }
 __global__ void k_count_u8(const uint8_t *m, int64_t n, int32_t *total)
 {
@@ -582,26 +615,26 @@ __global__ void k_count_u8(const uint8_t *m, int64_t n, int32_t *total)
 }
 }  // namespace
 
-int kp_prim_csum(kp_ctx *ctx, const double *d_x, int64_t n, double *d_tmp, double *d_out)
+int kp_prim_csum_mode(kp_ctx *ctx, const double *d_x, int64_t n, double *d_tmp, double *d_out, int mode, const double *d_aux,
+                      double aux_div)
 {
     if (n <= 0) {
         KP_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(double), ctx->stream));
         return KP_OK;
     }
-    const double *cur = d_x;
-    int64_t cn = n;
-    double *nxt = d_tmp;
-    for (;;) {
-        int64_t groups = (cn + 1023) / 1024;
-        double *dst = groups == 1 ? d_out : nxt;
-        k_csum_level<<<kp_blocks(groups, 8), 256, 0, ctx->stream>>>(cur, cn, dst, groups);
+    const int64_t groups = (n + 1023) / 1024;
+    k_csum_level<<<kp_blocks(groups, 8), 256, 0, ctx->stream>>>(d_x, n, groups == 1 ? d_out : d_tmp, groups, mode, d_aux, aux_div);
+    KP_LAUNCH_CHECK(ctx);
+    if (groups > 1) {
+        k_csum_rest<<<1, 1024, 0, ctx->stream>>>(d_tmp, groups, d_out);
         KP_LAUNCH_CHECK(ctx);
-        if (groups == 1) break;
-        cur = dst;
-        cn = groups;
-        nxt = dst + groups;
     }
     return KP_OK;
+}
+
+int kp_prim_csum(kp_ctx *ctx, const double *d_x, int64_t n, double *d_tmp, double *d_out)
+{
+    return kp_prim_csum_mode(ctx, d_x, n, d_tmp, d_out, 0, nullptr, 1.0);
 }
 
 int kp_prim_count_u8(kp_ctx *ctx, const uint8_t *d_mask, int64_t n, int32_t *d_total)
