@@ -36,9 +36,8 @@ struct kp_ctx {
     std::vector<cudaEvent_t> ev_pool;
     int sm_count = 148;
     // decoupled look-back state of the single-pass scans (kp_primitives.cu): one 64-bit word per tile
-    // {epoch:30, flag:2, value:32} + a ticket counter; never cleared between calls, the epoch invalidates old words
+    // {epoch:30, flag:2, value:32}; never cleared between calls, the epoch invalidates old words
     unsigned long long *d_lb_state = nullptr;
-    unsigned int *d_lb_ticket = nullptr;
     unsigned int lb_epoch = 0;
     static constexpr int LB_TILES = 1 << 16;
     int icp_passes_hint = 0;          // passes the last ICP on this context executed (sizes the next call's first batch)

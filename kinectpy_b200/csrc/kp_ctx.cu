@@ -50,7 +50,6 @@ int kp_ctx_create(int device, kp_ctx **out)
     KP_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, ctx->scratch_bytes, ctx->stream));
     KP_CUDA(ctx, cudaMalloc((void **)&ctx->d_lb_state, sizeof(unsigned long long) * kp_ctx::LB_TILES + 256));
     KP_CUDA(ctx, cudaMemsetAsync(ctx->d_lb_state, 0, sizeof(unsigned long long) * kp_ctx::LB_TILES + 256, ctx->stream));
-    ctx->d_lb_ticket = (unsigned int *)(ctx->d_lb_state + kp_ctx::LB_TILES);
     KP_CUDA(ctx, cudaEventCreate(&ctx->t0));
     KP_CUDA(ctx, cudaEventCreate(&ctx->t1));
     cudaDeviceProp prop;

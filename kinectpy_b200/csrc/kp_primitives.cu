@@ -176,7 +176,7 @@ __device__ __forceinline__ unsigned lb_exclusive(volatile unsigned long long *st
 
 template <class Flag, class Emit>
 __global__ void __launch_bounds__(SC_THREADS) k_flag_compact(int64_t n, Flag flag, Emit emit, unsigned long long *state,
-                                                             unsigned int *ticket, unsigned epoch, int32_t *total)
+                                                             unsigned epoch, int32_t *total)
 {
     __shared__ int cnt[SC_ITEMS * (SC_THREADS / 32)];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -242,7 +242,7 @@ int compact_generic(kp_ctx *ctx, int64_t n, Flag flag, Emit emit, int32_t *d_tot
     if (nb <= (unsigned)kp_ctx::LB_TILES) {
         unsigned epoch;
         KP_TRY(lb_next_epoch(ctx, &epoch));
-        k_flag_compact<<<nb, SC_THREADS, 0, ctx->stream>>>(n, flag, emit, ctx->d_lb_state, ctx->d_lb_ticket, epoch, d_total);
+        k_flag_compact<<<nb, SC_THREADS, 0, ctx->stream>>>(n, flag, emit, ctx->d_lb_state, epoch, d_total);
         KP_LAUNCH_CHECK(ctx);
         return KP_OK;
     }
@@ -318,10 +318,31 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K *keys, int64_t n
     hist[threadIdx.x] = 0;
     __syncthreads();
     int64_t base = (int64_t)blockIdx.x * RS_TILE;
+    if (base + RS_TILE <= n) {
+        // full tile: a thread takes RS_ITEMS CONSECUTIVE keys (16-byte loads) and sends one shared-memory atomic per
+        // run of equal digits.  Keys arrive spatially ordered, so above the lowest digit a thread's keys mostly
+        // share their digit: the kernel is bound by these atomics, and this halves them.
+        constexpr int PER16 = 16 / (int)sizeof(K), NV = RS_ITEMS / PER16;
+        const uint4 *src = reinterpret_cast<const uint4 *>(keys + base) + (int64_t)threadIdx.x * NV;
+        uint4 raw[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) raw[v] = src[v];
+        const K *kk = reinterpret_cast<const K *>(raw);
+        unsigned run_d = (unsigned)(kk[0] >> shift) & 0xFFu;
+        int run_n = 1;
+#pragma unroll
+        for (int j = 1; j < RS_ITEMS; ++j) {
+            const unsigned d = (unsigned)(kk[j] >> shift) & 0xFFu;
+            if (d == run_d) ++run_n;
+            else { atomicAdd(&hist[run_d], run_n); run_d = d; run_n = 1; }
+        }
+        atomicAdd(&hist[run_d], run_n);
+    } else {
 #pragma unroll 4
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        int64_t i = base + j * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&hist[(unsigned)(keys[i] >> shift) & 0xFFu], 1);
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            int64_t i = base + j * RS_THREADS + threadIdx.x;
+            if (i < n) atomicAdd(&hist[(unsigned)(keys[i] >> shift) & 0xFFu], 1);
+        }
     }
     __syncthreads();
     g_hist[(int64_t)threadIdx.x * nb + blockIdx.x] = hist[threadIdx.x];
