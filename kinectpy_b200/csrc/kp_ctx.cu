@@ -48,8 +48,8 @@ int kp_ctx_create(int device, kp_ctx **out)
     KP_CUDA(ctx, cudaMallocHost((void **)&ctx->h_scratch, ctx->scratch_bytes));
     KP_CUDA(ctx, cudaMalloc((void **)&ctx->d_scratch, ctx->scratch_bytes));
     KP_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, ctx->scratch_bytes, ctx->stream));
-    KP_CUDA(ctx, cudaMalloc((void **)&ctx->d_lb_state, sizeof(unsigned long long) * kp_ctx::LB_TILES + 256));
-    KP_CUDA(ctx, cudaMemsetAsync(ctx->d_lb_state, 0, sizeof(unsigned long long) * kp_ctx::LB_TILES + 256, ctx->stream));
+    KP_CUDA(ctx, cudaMalloc((void **)&ctx->d_lb_state, sizeof(unsigned long long) * (kp_ctx::LB_TILES + kp_ctx::LB_TILES / 32 + 32)));
+    KP_CUDA(ctx, cudaMemsetAsync(ctx->d_lb_state, 0, sizeof(unsigned long long) * (kp_ctx::LB_TILES + kp_ctx::LB_TILES / 32 + 32), ctx->stream));
     KP_CUDA(ctx, cudaEventCreate(&ctx->t0));
     KP_CUDA(ctx, cudaEventCreate(&ctx->t1));
     cudaDeviceProp prop;

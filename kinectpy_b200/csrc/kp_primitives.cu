@@ -131,47 +131,46 @@ __global__ void __launch_bounds__(SC_THREADS) k_flag_scatter(int64_t n, Flag fla
     }
 }
 
-// ---- decoupled look-back (single-pass scan): tile t publishes its aggregate, then walks back over its
-// predecessors' words (32 at a time, one per lane) until it meets an inclusive prefix.  A word carries
-// {epoch:30, flag:2, value:32}; words of earlier calls have another epoch and read as "not ready", so the state
-// array is never cleared.
-constexpr unsigned LB_AGG = 1u, LB_INCL = 2u;
+// ---- single-pass scan: tile offsets in two levels.  Tile t publishes its aggregate; the last tile of every group
+// of 32 adds its group's aggregates and publishes the group total; tile t's exclusive prefix is then (totals of
+// the groups before it) + (aggregates of the tiles before it in its own group): two dependent reads, whatever t
+// is.  (A frame's arrays are a few hundred tiles that are all resident and in step.  A classic decoupled
+// look-back, where a tile walks back until it meets a finished predecessor, was measured first: inclusive prefixes
+// appear late in that regime, tiles near the end made ~17 dependent round trips, and 62 % of the kernel was the
+// other warps waiting at the barrier behind that walk.)  A word carries {epoch:30, flag:2, value:32}; words of
+// earlier calls have another epoch and read as "not ready", so the state arrays are never cleared.  Tiles are
+// numbered by blockIdx.x (see k_flag_compact), so every tile a running tile waits for has started.
+constexpr unsigned LB_READY = 1u;
 __device__ __forceinline__ unsigned long long lb_pack(unsigned epoch, unsigned flag, unsigned v)
 {
     return ((unsigned long long)((epoch << 2) | flag) << 32) | v;
 }
-// executed by one full warp; returns the exclusive prefix of `tile` to every lane
+__device__ __forceinline__ unsigned lb_wait(volatile unsigned long long *word, unsigned epoch)
+{
+    unsigned long long x;
+    do { x = *word; } while ((unsigned)(x >> 34) != epoch);
+    return (unsigned)x;
+}
+// executed by one full warp; returns the exclusive prefix of `tile` to every lane.
+// state: [LB_TILES] tile aggregates, then [LB_TILES / 32] group totals.
 __device__ __forceinline__ unsigned lb_exclusive(volatile unsigned long long *state, unsigned tile, unsigned agg,
                                                  unsigned epoch, int lane)
 {
-    if (tile == 0) {
-        if (lane == 0) state[0] = lb_pack(epoch, LB_INCL, agg);
-        return 0u;
-    }
-    if (lane == 0) state[tile] = lb_pack(epoch, LB_AGG, agg);
-    unsigned excl = 0;
-    int pos = (int)tile - 1;
-    for (;;) {
-        const int idx = pos - lane;
-        unsigned flag = LB_INCL, val = 0;           // lanes that ran off the front: an inclusive prefix of 0
-        if (idx >= 0) {
-            unsigned long long w;
-            do { w = state[idx]; } while ((unsigned)(w >> 34) != epoch);
-            flag = (unsigned)(w >> 32) & 3u;
-            val = (unsigned)w;
-        }
-        const unsigned incl_mask = __ballot_sync(KP_FULL, flag == LB_INCL);
-        const int first = __ffs(incl_mask) - 1;     // nearest predecessor holding an inclusive prefix
-        const unsigned take = first < 0 ? KP_FULL : ((2u << first) - 1u);
-        unsigned v = ((take >> lane) & 1u) ? val : 0u;
+    volatile unsigned long long *gstate = state + kp_ctx::LB_TILES;
+    if (lane == 0) state[tile] = lb_pack(epoch, LB_READY, agg);
+    const unsigned g = tile >> 5, r = tile & 31u;
+    // the tiles before me in my group first: a group total must not wait for the totals of the groups before it
+    unsigned in_group = (unsigned)lane < r ? lb_wait(state + (g << 5) + lane, epoch) : 0u;
 #pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(KP_FULL, v, s);
-        excl += v;
-        if (first >= 0) break;
-        pos -= 32;
-    }
-    if (lane == 0) state[tile] = lb_pack(epoch, LB_INCL, excl + agg);
-    return excl;
+    for (int s = 16; s >= 1; s >>= 1) in_group += __shfl_xor_sync(KP_FULL, in_group, s);
+    if (r == 31u && lane == 0) gstate[g] = lb_pack(epoch, LB_READY, in_group + agg);
+    // then the totals of the groups before mine
+    unsigned v = 0;
+    for (unsigned base = 0; base < g; base += 32)
+        if (base + lane < g) v += lb_wait(gstate + base + lane, epoch);
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(KP_FULL, v, s);
+    return v + in_group;
 }
 
 template <class Flag, class Emit>
@@ -224,7 +223,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_flag_compact(int64_t n, Flag fla
 int lb_next_epoch(kp_ctx *ctx, unsigned *epoch)
 {
     if (++ctx->lb_epoch >= (1u << 30)) {
-        KP_CUDA(ctx, cudaMemsetAsync(ctx->d_lb_state, 0, sizeof(unsigned long long) * kp_ctx::LB_TILES, ctx->stream));
+        KP_CUDA(ctx, cudaMemsetAsync(ctx->d_lb_state, 0, sizeof(unsigned long long) * (kp_ctx::LB_TILES + kp_ctx::LB_TILES / 32), ctx->stream));
         ctx->lb_epoch = 1;
     }
     *epoch = ctx->lb_epoch;
