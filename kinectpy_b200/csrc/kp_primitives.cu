@@ -381,6 +381,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K *keys_in, con
     __shared__ int cnt[RS_WARPS][256];
     __shared__ int dig_wtot[RS_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // digit threadIdx.x: its total and this tile's offset inside it are requested now, used after the ranking
+    const int dig_tot = g_tot[threadIdx.x];
+    const int dig_off = g_hist[(int64_t)threadIdx.x * nb + blockIdx.x];
     for (int e = threadIdx.x; e < RS_WARPS * 256; e += RS_THREADS) (&cnt[0][0])[e] = 0;
     __syncthreads();
     const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * (RS_ITEMS * 32);
@@ -418,7 +421,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K *keys_in, con
     {
         int d = threadIdx.x;   // 256 threads <-> 256 digits
         // global base of digit d = exclusive scan over the 256 digit totals (block scan, recomputed per tile)
-        int tot = g_tot[d], incl = tot;
+        int tot = dig_tot, incl = tot;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
             int y = __shfl_up_sync(KP_FULL, incl, s);
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K *keys_in, con
         int base = incl - tot;
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ++ww) base += ww < w ? dig_wtot[ww] : 0;
-        int off = base + g_hist[(int64_t)d * nb + blockIdx.x];
+        int off = base + dig_off;
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ++ww) { int c = cnt[ww][d]; cnt[ww][d] = off; off += c; }
     }
