@@ -266,20 +266,27 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __
     __shared__ double tot[ICP_NV];
     __shared__ unsigned int s_ticket;
     IcpState *st = p.st;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * ICP_THREADS + tid;
+    // the point, its last partner and the state words are requested together: one memory round trip before the
+    // first arithmetic instead of two (a pass launched after `done` only wastes these few loads)
+    double sx0 = 0.0, sy0 = 0.0, sz0 = 0.0;
+    int prev0 = -1;
+    if (i < p.ns) {
+        sx0 = p.cur[3 * (int64_t)i]; sy0 = p.cur[3 * (int64_t)i + 1]; sz0 = p.cur[3 * (int64_t)i + 2];
+        prev0 = p.corr[i];              // (not yet written in pass 0: ignored there)
+    }
     if (st->done) return;
     const int pass = st->pass;          // advanced only after every CTA has taken its ticket
     const KpGridDev &g = p.g;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = blockIdx.x * ICP_THREADS + tid;
     bool has = false;
     // plane / colored: J (6) and r of the geometric term; colored adds the photometric row J2, r2;
     // point-to-point: J[0..2] = s, J[3..5] = t
     double J[6] = {0, 0, 0, 0, 0, 0}, r = 0.0, bd = 0.0;
     double J2[6] = {0, 0, 0, 0, 0, 0}, r2v = 0.0;
     if (i < p.ns) {
-        double sx = p.cur[3 * (int64_t)i], sy = p.cur[3 * (int64_t)i + 1], sz = p.cur[3 * (int64_t)i + 2];
-        // last pass's partner is requested with the point itself (not after the update has been computed and stored)
-        int prev = pass > 0 ? p.corr[i] : -1;
+        double sx = sx0, sy = sy0, sz = sz0;
+        int prev = pass > 0 ? prev0 : -1;
         if (pass > 0) {
             const double *U = st->U;
             const double x2 = kp_affine(U[0], U[1], U[2], U[3], sx, sy, sz);
