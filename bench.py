@@ -127,6 +127,8 @@ def cpu_baseline(cfg, depth, tab, T_fuse, T_icp, frames):
     """The oracle port (oracle/kp_oracle.c, OpenMP over all host cores) on a bounded sample of the workload."""
     from oracle import oracle as orc
     orc.build()
+    # every host thread this process may use, whatever OMP_NUM_THREADS a launcher exported
+    orc.set_num_threads(int(os.environ.get("KP_REF_THREADS", len(os.sched_getaffinity(0)))))
     t0 = time.perf_counter()
     tm = {}
     for f in range(frames):
@@ -167,9 +169,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm runs alone on rank 0 and is meant to use every
+        # host thread it can get (KP_REF_THREADS overrides).  Set before the OpenMP runtime of the oracle library loads.
+        os.environ["OMP_NUM_THREADS"] = os.environ.get("KP_REF_THREADS", str(cores))
         _, depth, tab, T_fuse, T_icp = make_inputs(args.mode, min(args.distinct_frames, 2), 0)
         from oracle import oracle as orc
         orc.build()
+        orc.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
         for _ in range(min(args.warmup, 1)):
             orc.frame_pipeline(cfg, depth[0], tab, T_fuse, T_icp)
         t0 = time.perf_counter()

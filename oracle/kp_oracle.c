@@ -1251,6 +1251,16 @@ KPO_API int kpo_ransac_correspondence(const float *src, const float *tgt, const 
     return 0;
 }
 
+/* threads the OpenMP loops of this library use from now on (a launcher may have exported OMP_NUM_THREADS=1) */
+KPO_API void kpo_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 KPO_API int kpo_num_threads(void)
 {
 #ifdef _OPENMP

@@ -68,6 +68,11 @@ def num_threads() -> int:
     return int(lib().kpo_num_threads())
 
 
+def set_num_threads(n: int) -> None:
+    """OpenMP threads of the oracle's loops (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().kpo_set_num_threads(C.c_int(int(n)))
+
+
 def rng(seed, a, b) -> int:
     return int(lib().kpo_rng(C.c_uint64(seed), C.c_uint64(a), C.c_uint64(b)))
 
