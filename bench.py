@@ -144,13 +144,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # Host side of the frame pipeline: one worker thread per frame in flight.  A worker waits for its stream ~15
-    # times per frame; spinning waits are fastest while each worker has a core of its own, sleeping waits
-    # (measured: same throughput with 8 frames in flight instead of 6) when the ranks of the box outnumber its cores.
+    # Host side of the frame pipeline: one worker thread per frame in flight.  A worker waits for its stream ~12
+    # times per frame; spinning waits are fastest while the box has cores to spare, sleeping waits (measured: 8 frames
+    # in flight sleeping reach 97 % of 6 spinning) when the workers of all ranks together would crowd the cores.
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(max(world, 1))))
     if "KP_SYNC" not in os.environ:
-        os.environ["KP_SYNC"] = "block" if cores < local_world * 7 else "spin"
+        # measured: 14 spinning workers on 24 cores scale 2.01 x over one GPU, 28 on 32 cores only 3.60 x over four:
+        # spin only while the box's workers stay under ~60 % of its cores
+        os.environ["KP_SYNC"] = "block" if local_world * 7 * 10 > cores * 6 else "spin"
     if args.streams <= 0:
         args.streams = 8 if os.environ["KP_SYNC"] == "block" else 6
     if args.frames_per_step <= 0:
