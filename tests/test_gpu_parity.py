@@ -117,9 +117,10 @@ def test_transform_bounds_compact(ctx, oracle):
 
 @pytest.mark.parametrize("n", [1, 31, 2047, 2048, 2049, 65536, 300007])
 def test_compact_single_pass_scan_across_tiles(ctx, n):
-    """Ordered compaction is one kernel: tiles of 2048 chained by a decoupled look-back whose per-tile words are
-    tagged with a per-call epoch (never cleared).  Ragged sizes around the tile edge, sparse / dense / run-structured
-    masks, and back-to-back calls on the same context (stale words of earlier calls must read as 'not ready')."""
+    """Ordered compaction is one kernel: tiles of 2048 whose offsets come from published tile aggregates and group
+    totals (groups of 32 tiles), each word tagged with a per-call epoch (never cleared).  Ragged sizes around the tile
+    and group edges, sparse / dense / run-structured masks, and back-to-back calls on the same context (stale words
+    of earlier calls must read as 'not ready')."""
     rng = np.random.default_rng(n)
     pts = rng.random((n, 3), dtype=np.float32)
     masks = [(rng.random(n) < p).astype(np.uint8) for p in (0.001, 0.5, 0.999)]
