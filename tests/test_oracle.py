@@ -216,6 +216,62 @@ def test_icp_recovers_planted_transform(oracle):
     assert np.array_equal(r0["T"], D) and r0["iters"] == 0
 
 
+def _numpy_p2plane_icp(src, tgt, nrm, max_corr, init, max_iter, rel_fit=1e-6, rel_rmse=1e-6):
+    """Open3D's RegistrationICP + TransformationEstimationPointToPlane written out independently:
+    cKDTree 1-NN inside max_corr, r = (s - t).n, J = [s x n, n], JtJ x = -Jtr, T <- (Rz Ry Rx | t)(x) T, stop when both
+    fitness and rmse move by less than the relative thresholds."""
+    from scipy.spatial import cKDTree
+    tree = cKDTree(tgt.astype(np.float64))
+    T = np.array(init, np.float64)
+    cur = src.astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+
+    def correspondences(p):
+        d, j = tree.query(p, k=1, distance_upper_bound=max_corr)
+        ok = np.isfinite(d) & (d < max_corr)
+        return ok, j, d
+
+    ok, j, d = correspondences(cur)
+    fit, rmse = ok.mean(), (np.sqrt((d[ok] ** 2).mean()) if ok.any() else 0.0)
+    iters = 0
+    for it in range(max_iter):
+        s, t, n = cur[ok], tgt[j[ok]].astype(np.float64), nrm[j[ok]].astype(np.float64)
+        r = ((s - t) * n).sum(1)
+        J = np.hstack([np.cross(s, n), n])
+        x = np.linalg.solve(J.T @ J, -(J.T @ r))
+        ca, sa, cb, sb, cg, sg = np.cos(x[0]), np.sin(x[0]), np.cos(x[1]), np.sin(x[1]), np.cos(x[2]), np.sin(x[2])
+        U = np.eye(4)
+        U[:3, :3] = [[cg * cb, cg * sb * sa - sg * ca, cg * sb * ca + sg * sa],
+                     [sg * cb, sg * sb * sa + cg * ca, sg * sb * ca - cg * sa],
+                     [-sb, cb * sa, cb * ca]]
+        U[:3, 3] = x[3:]
+        T = U @ T
+        cur = cur @ U[:3, :3].T + U[:3, 3]
+        ok, j, d = correspondences(cur)
+        nfit, nrmse = ok.mean(), (np.sqrt((d[ok] ** 2).mean()) if ok.any() else 0.0)
+        iters = it + 1
+        done = abs(fit - nfit) < rel_fit and abs(rmse - nrmse) < rel_rmse
+        fit, rmse = nfit, nrmse
+        if done:
+            break
+    return T, fit, rmse, iters
+
+
+def test_icp_vs_independent_numpy_restatement(oracle):
+    """The oracle's ICP against a from-scratch NumPy / cKDTree transcription of the upstream loop: same iteration count,
+    same fitness, transforms equal to rounding (the two differ only in summation order and in the linear solver)."""
+    from kinectpy_b200 import synth
+    tgt = make_surface_cloud(5000, seed=21, outliers=0.0)
+    nrm = oracle.estimate_normals(tgt, 0.1, 30)
+    D = synth.perturbed_extrinsic(np.eye(4), angle_deg=0.8, shift_mm=(4, -3, 5), unit_scale=1e-3)
+    src = oracle.transform(tgt[1::2], np.linalg.inv(D))
+    for max_corr, max_iter in ((0.05, 30), (0.02, 5)):
+        res = oracle.icp_point_to_plane(src, tgt, nrm, max_corr, init=np.eye(4), max_iter=max_iter)
+        T, fit, rmse, iters = _numpy_p2plane_icp(src, tgt, nrm, max_corr, np.eye(4), max_iter)
+        assert res["iters"] == iters
+        assert abs(res["fitness"] - fit) < 1e-12 and abs(res["rmse"] - rmse) < 1e-9
+        assert np.abs(res["T"] - T).max() < 1e-9
+
+
 def test_unproject_modes(oracle):
     from kinectpy_b200 import synth
     depth, tab, T = synth.render_sequence(synth.NFOV, 1, 2)
