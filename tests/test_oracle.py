@@ -170,6 +170,33 @@ def test_normals_on_plane(oracle):
     assert oracle.estimate_normals(lonely, 0.1, 30).tolist() == [[0, 0, 1], [0, 0, 1]]
 
 
+def test_normals_vs_independent_hybrid_search(oracle):
+    """estimate_normals(KDTreeSearchParamHybrid(r, max_nn)) written out independently: the max_nn nearest points
+    strictly inside r (the point itself included), covariance from the cumulants, smallest-eigenvalue eigenvector
+    by numpy.linalg.eigh; fewer than 3 neighbours -> (0, 0, 1).  Compared modulo sign where the eigen-gap is clear."""
+    pts = make_surface_cloud(3000, seed=31, outliers=0.01)
+    radius, max_nn = 0.06, 30
+    out = oracle.estimate_normals(pts, radius, max_nn)
+    P = pts.astype(np.float64)
+    tree = cKDTree(P)
+    d, j = tree.query(P, k=max_nn, distance_upper_bound=radius * (1 - 1e-12))
+    checked = 0
+    for i in range(len(P)):
+        nb = j[i][np.isfinite(d[i])]
+        if len(nb) < 3:
+            assert out[i].tolist() == [0, 0, 1]
+            continue
+        q = P[nb]
+        m = q.mean(0)
+        cov = (q[:, :, None] * q[:, None, :]).mean(0) - np.outer(m, m)
+        w, V = np.linalg.eigh(cov)
+        if w[1] - w[0] < 1e-3 * w[2]:
+            continue                                    # near-degenerate: the direction is not defined
+        assert abs(abs(out[i].astype(np.float64) @ V[:, 0]) - 1.0) < 1e-5
+        checked += 1
+    assert checked > 0.6 * len(P)
+
+
 def test_ransac_plane(oracle):
     r = np.random.default_rng(12)
     n = 5000
