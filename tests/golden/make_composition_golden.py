@@ -1,0 +1,204 @@
+#!/usr/bin/env python
+"""Generate tests/golden/reference_compositions.npz by RUNNING THE REFERENCE'S OWN WRAPPERS
+(/root/reference, read-only) in this container.
+
+Open3D is absent here, so the reference's wrapper code is executed, unmodified, against an ``open3d`` stand-in
+whose geometry routines are the CPU oracle's (oracle/kp_oracle.c).  What this pins is everything the WRAPPERS
+decide -- which routine is called on which cloud, in which order, with which arguments and defaults, what is
+copied and what is returned:
+
+* ``preprocessing.filtering.filter_outliers``                         (preprocessing/filtering.py:12-25)
+* ``preprocessing.registration.execute_point_to_plane_registration`` (preprocessing/registration.py:65-86, through
+  ``prepare_dataset`` / ``preprocess_point_cloud`` :7-29 -- note the double source/target swap)
+* the floor-removal body of ``floor_removal.py`` (:63-73), exec'd verbatim from the file's own source lines
+
+tests/test_golden.py then checks that the oracle's array-level compositions (``oracle.filter_outliers``,
+``oracle.remove_floor``, and the registration composition the frame pipeline uses) reproduce these outputs;
+the GPU tests compare the kernels with those compositions.
+
+Run:  python tests/golden/make_composition_golden.py     (needs /root/reference; the .npz is committed)
+"""
+import contextlib
+import copy
+import io
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+OUT = os.path.join(HERE, "reference_compositions.npz")
+sys.path.insert(0, ROOT)
+
+CALLS = []          # (routine, arguments) in the order the reference's wrappers made them
+
+
+def oracle_backed_namespace():
+    """(PointCloud, registration namespace, geometry namespace): the slice of Open3D the wrappers touch, computed by the oracle."""
+    from oracle import oracle as orc
+
+    class PointCloud:
+        def __init__(self, points=None):
+            self.points = np.zeros((0, 3)) if points is None else np.asarray(points, dtype=np.float64)
+            self.colors = np.zeros((0, 3))
+            self.normals = np.zeros((0, 3))
+
+        def has_normals(self):
+            return len(self.normals) == len(self.points) and len(self.points) > 0
+
+        def voxel_down_sample(self, voxel_size):
+            CALLS.append(("voxel_down_sample", float(voxel_size), len(self.points)))
+            v = orc.voxel_downsample(self.points, float(voxel_size))
+            return PointCloud(v["points"])
+
+        def remove_statistical_outlier(self, nb_neighbors, std_ratio):
+            CALLS.append(("remove_statistical_outlier", int(nb_neighbors), float(std_ratio), len(self.points)))
+            keep, _, _ = orc.sor(self.points, int(nb_neighbors), float(std_ratio))
+            idx = np.flatnonzero(keep)
+            return self.select_by_index(idx), idx.tolist()
+
+        def estimate_normals(self, search_param):
+            CALLS.append(("estimate_normals", float(search_param.radius), int(search_param.max_nn), len(self.points)))
+            self.normals = orc.estimate_normals(self.points, float(search_param.radius), int(search_param.max_nn)).astype(np.float64)
+
+        def segment_plane(self, distance_threshold, ransac_n, num_iterations):
+            CALLS.append(("segment_plane", float(distance_threshold), int(ransac_n), int(num_iterations), len(self.points)))
+            plane, mask, _, _ = orc.ransac_plane(self.points, float(distance_threshold), int(ransac_n), int(num_iterations),
+                                                 seed=1234)
+            return plane, np.flatnonzero(mask).tolist()
+
+        def select_by_index(self, indices, invert=False):
+            idx = np.asarray(indices, dtype=np.int64).reshape(-1)
+            mask = np.zeros(len(self.points), dtype=bool)
+            mask[idx] = True
+            if invert:
+                mask = ~mask
+            out = PointCloud(np.asarray(self.points)[mask])
+            if self.has_normals():
+                out.normals = np.asarray(self.normals)[mask]
+            return out
+
+        def transform(self, T):
+            self.points = orc.transform(self.points, T).astype(np.float64)
+            return self
+
+        def __add__(self, other):
+            return PointCloud(np.concatenate([np.asarray(self.points), np.asarray(other.points)], axis=0))
+
+    class Hybrid:
+        def __init__(self, radius, max_nn):
+            self.radius, self.max_nn = radius, max_nn
+
+    class PointToPlane:
+        pass
+
+    class Result:
+        pass
+
+    def registration_icp(source, target, threshold, init, estimation, *rest):
+        assert isinstance(estimation, PointToPlane) and target.has_normals()
+        CALLS.append(("registration_icp", float(threshold), len(source.points), len(target.points)))
+        r = orc.icp_point_to_plane(source.points, target.points, target.normals, float(threshold), init=init, max_iter=30)
+        out = Result()
+        out.transformation, out.fitness, out.inlier_rmse = r["T"], r["fitness"], r["rmse"]
+        return out
+
+    def compute_fpfh_feature(pcd, search_param):
+        CALLS.append(("compute_fpfh_feature", float(search_param.radius), int(search_param.max_nn), len(pcd.points)))
+        return None             # not consumed by the point-to-plane refinement
+
+    registration = types.SimpleNamespace(registration_icp=registration_icp, TransformationEstimationPointToPlane=PointToPlane,
+                                         compute_fpfh_feature=compute_fpfh_feature)
+    geometry = types.SimpleNamespace(PointCloud=PointCloud, KDTreeSearchParamHybrid=Hybrid)
+    return PointCloud, registration, geometry
+
+
+def install_oracle_backed_open3d():
+    PointCloud, registration, geometry = oracle_backed_namespace()
+    o3d = types.ModuleType("open3d")
+    o3d.geometry = geometry
+    o3d.utility = types.SimpleNamespace(Vector3dVector=lambda a: np.asarray(a, dtype=np.float64))
+    o3d.pipelines = types.SimpleNamespace(registration=registration)
+    o3d.visualization = types.SimpleNamespace()
+    o3d.io = types.SimpleNamespace()
+    sys.modules["open3d"] = o3d
+    for name in ("tensorflow", "imghdr", "PIL", "PIL.Image", "cv2"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["PIL"].Image = sys.modules["PIL.Image"]
+    return PointCloud
+
+
+def scene(n, seed, mm=False):
+    """A floor (y = max), a wall and a blob standing on the floor, plus a few stray points; metres or millimetres."""
+    r = np.random.default_rng(seed)
+    floor = np.stack([r.uniform(-1, 1, n // 2), 1.2 + r.normal(0, 0.002, n // 2), r.uniform(1, 3, n // 2)], 1)
+    wall = np.stack([r.uniform(-1, 1, n // 4), r.uniform(-0.8, 1.2, n // 4), 3.0 + r.normal(0, 0.002, n // 4)], 1)
+    blob = r.normal(0, 0.12, (n // 4, 3)) * [1, 3, 1] + [0, 0.7, 2.0]
+    blob[:, 1] = np.minimum(blob[:, 1], 1.19)          # it stands on the floor, nothing lies below it
+    stray = r.uniform(-1, 1, (n // 100, 3)) + [0, 0, 2]
+    pts = np.concatenate([floor, wall, blob, stray], 0)
+    return (pts * (1000.0 if mm else 1.0)).astype(np.float32)
+
+
+def main():
+    PointCloud = install_oracle_backed_open3d()
+    sys.path.insert(0, REF)
+    from preprocessing import filtering as ref_filtering
+    from preprocessing import registration as ref_registration
+    out = {}
+
+    # ---- filter_outliers: explicit arguments (BASELINE config 1) and the reference's defaults (units: metres / mm)
+    pts = scene(6000, 1)
+    del CALLS[:]
+    got = ref_filtering.filter_outliers(PointCloud(pts), nb_neighbors=20, std_ratio=2.0, voxel_size=0.02)
+    out["fo_in"], out["fo_out"] = pts, np.asarray(got.points, np.float32)
+    out["fo_calls"] = np.array(repr(CALLS))
+    pts_mm = scene(6000, 2, mm=True)
+    del CALLS[:]
+    src = PointCloud(pts_mm)
+    got = ref_filtering.filter_outliers(src)          # defaults 200 / 3.0 / 0.02: on mm data every point is its own voxel
+    out["fo_default_in"], out["fo_default_out"] = pts_mm, np.asarray(got.points, np.float32)
+    out["fo_default_calls"] = np.array(repr(CALLS))
+    assert np.array_equal(np.asarray(src.points, np.float32), pts_mm)       # the input cloud is not modified
+
+    # ---- execute_point_to_plane_registration (mm units, the reference's voxel 35 / threshold 100)
+    from kinectpy_b200 import synth
+    master = scene(8000, 3, mm=True)
+    D = synth.perturbed_extrinsic(np.eye(4), angle_deg=1.0, shift_mm=(12, -8, 10), unit_scale=1.0)
+    from oracle import oracle as orc
+    sub = orc.transform(scene(8000, 4, mm=True), np.linalg.inv(D))
+    init = np.eye(4)
+    del CALLS[:]
+    with contextlib.redirect_stdout(io.StringIO()):
+        T = ref_registration.execute_point_to_plane_registration(PointCloud(master), PointCloud(sub), init, voxel_size=35)
+    out["reg_master"], out["reg_sub"], out["reg_init"], out["reg_T"] = master, sub, init, np.asarray(T, np.float64)
+    out["reg_calls"] = np.array(repr(CALLS))
+
+    # ---- floor removal: the body of the script's loop, exec'd verbatim from the reference's file
+    src_lines = open(os.path.join(REF, "floor_removal.py")).read().splitlines()
+    main_at = next(i for i, ln in enumerate(src_lines) if ln.startswith("if __name__"))
+    first = next(i for i, ln in enumerate(src_lines) if i > main_at and "pcd_points = np.asarray(pcd.points)" in ln)
+    last = next(i for i, ln in enumerate(src_lines) if i > main_at and "remove_statistical_outlier(" in ln)
+    body = "\n".join(ln[8:] if ln.startswith(" " * 8) else ln.strip() for ln in src_lines[first:last + 1])
+    floor_in = scene(9000, 5, mm=True)
+    ns = {"np": np, "pcd": PointCloud(floor_in)}
+    del CALLS[:]
+    exec(body, ns)
+    out["floor_in"] = floor_in
+    out["floor_out"] = np.asarray(ns["filtered_pcd"].points, np.float32)
+    out["floor_plane"] = np.asarray(ns["plane_model"], np.float64)
+    out["floor_inliers"] = np.asarray(ns["inliers"], np.int64)
+    out["floor_calls"] = np.array(repr(CALLS))
+    out["floor_source"] = np.array(body)
+
+    np.savez_compressed(OUT, **out)
+    for k in ("fo_calls", "fo_default_calls", "reg_calls", "floor_calls"):
+        print(k, out[k])
+    print("wrote", OUT, {k: getattr(v, "shape", None) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -87,3 +87,73 @@ def test_gpu_floor_band_matches_reference():
     lower, upper = split_floor_band(PointCloud(GOLD["band_cloud"]), 200)
     assert np.array_equal(np.asarray(lower.points), GOLD["band_cloud"][GOLD["band_lower_idx"]])
     assert np.array_equal(np.asarray(upper.points), GOLD["band_cloud"][GOLD["band_upper_idx"]])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Wrapper-level goldens: tests/golden/reference_compositions.npz was produced by the reference's OWN wrapper functions
+# (preprocessing/filtering.py, preprocessing/registration.py, the loop body of floor_removal.py) driving an `open3d`
+# stand-in computed by the oracle (tests/golden/make_composition_golden.py).  They pin what the wrappers decide:
+# call order, arguments and defaults, source / target roles, what is copied and returned.
+def _compositions():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_compositions.npz"))
+
+
+def _oracle_backed():
+    import importlib.util
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_composition_golden.py")
+    spec = importlib.util.spec_from_file_location("make_composition_golden", p)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_oracle_filter_outliers_composition_matches_reference_wrapper(oracle):
+    g = _compositions()
+    assert np.array_equal(oracle.filter_outliers(g["fo_in"], nb_neighbors=20, std_ratio=2.0, voxel_size=0.02), g["fo_out"])
+    assert np.array_equal(oracle.filter_outliers(g["fo_default_in"]), g["fo_default_out"])      # 200 / 3.0 / 0.02
+    assert "('voxel_down_sample', 0.02, 6060), ('remove_statistical_outlier', 200, 3.0, 6060)" in str(g["fo_default_calls"])
+
+
+def test_oracle_remove_floor_composition_matches_reference_script(oracle):
+    g = _compositions()
+    pts, plane, inl = oracle.remove_floor(g["floor_in"])          # the script's literals are the defaults
+    assert np.array_equal(pts, g["floor_out"])
+    assert np.array_equal(plane, g["floor_plane"]) and np.array_equal(np.flatnonzero(inl), g["floor_inliers"])
+    assert "('segment_plane', 30.0, 30, 2000," in str(g["floor_calls"]) and "('remove_statistical_outlier', 50, 0.3," in str(g["floor_calls"])
+
+
+def test_mirror_wrappers_make_the_reference_wrappers_calls(oracle, monkeypatch):
+    """Our Python mirrors (kinectpy_b200.preprocessing.*) run against the SAME oracle-backed stand-in the reference's
+    wrappers ran against: identical results and identical call traces (the mirror skips the FPFH the reference
+    computes and throws away), the input clouds untouched.  No GPU involved: this is about the wrappers' logic."""
+    mod = _oracle_backed()
+    PointCloud, registration, geometry = mod.oracle_backed_namespace()
+    from kinectpy_b200.preprocessing import filtering as our_filtering
+    from kinectpy_b200.preprocessing import registration as our_registration
+    g = _compositions()
+    # filter_outliers
+    del mod.CALLS[:]
+    src = PointCloud(g["fo_in"])
+    got = our_filtering.filter_outliers(src, nb_neighbors=20, std_ratio=2.0, voxel_size=0.02)
+    assert np.array_equal(np.asarray(got.points, np.float32), g["fo_out"])
+    assert repr(mod.CALLS) == str(g["fo_calls"]) and np.array_equal(np.asarray(src.points, np.float32), g["fo_in"])
+    del mod.CALLS[:]
+    got = our_filtering.filter_outliers(PointCloud(g["fo_default_in"]))
+    assert np.array_equal(np.asarray(got.points, np.float32), g["fo_default_out"]) and repr(mod.CALLS) == str(g["fo_default_calls"])
+    # execute_point_to_plane_registration: sub is the ICP source, master the target (the reference's double swap)
+    ns = type("G", (), {})()
+    for k, v in list(vars(registration).items()) + list(vars(geometry).items()):
+        setattr(ns, k, v)
+    monkeypatch.setattr(our_registration, "_g", ns)
+    del mod.CALLS[:]
+    master, sub = PointCloud(g["reg_master"]), PointCloud(g["reg_sub"])
+    T = our_registration.execute_point_to_plane_registration(master, sub, g["reg_init"], voxel_size=35)
+    assert np.array_equal(np.asarray(T, np.float64), g["reg_T"])
+    ref_calls = [c for c in eval(str(g["reg_calls"])) if c[0] != "compute_fpfh_feature"]
+    assert mod.CALLS == ref_calls
+    assert np.array_equal(np.asarray(master.points, np.float32), g["reg_master"]) and not master.has_normals()
+    # and the array-level composition the frame pipeline implements (oracle pieces, same roles)
+    src_d = oracle.voxel_downsample(g["reg_sub"], 35.0)["points"]
+    tgt_d = oracle.voxel_downsample(g["reg_master"], 35.0)["points"]
+    res = oracle.icp_point_to_plane(src_d, tgt_d, oracle.estimate_normals(tgt_d, 70.0, 40), 100.0, init=g["reg_init"], max_iter=30)
+    assert np.array_equal(res["T"], g["reg_T"])
