@@ -11,6 +11,8 @@ copied and what is returned:
 * ``preprocessing.registration.execute_point_to_plane_registration`` (preprocessing/registration.py:65-86, through
   ``prepare_dataset`` / ``preprocess_point_cloud`` :7-29 -- note the double source/target swap)
 * the floor-removal body of ``floor_removal.py`` (:63-73), exec'd verbatim from the file's own source lines
+* the fusion body of ``DataProcessor``'s frame loop (preprocessing/data.py:41-61), exec'd verbatim likewise
+* ``utils.processing.statistical_outlier_removal``                    (utils/processing.py:302-310)
 
 tests/test_golden.py then checks that the oracle's array-level compositions (``oracle.filter_outliers``,
 ``oracle.remove_floor``, and the registration composition the frame pipeline uses) reproduce these outputs;
@@ -82,6 +84,7 @@ def oracle_backed_namespace():
             return out
 
         def transform(self, T):
+            CALLS.append(("transform", np.asarray(T, np.float64).round(12).tolist(), len(self.points)))
             self.points = orc.transform(self.points, T).astype(np.float64)
             return self
 
@@ -194,8 +197,38 @@ def main():
     out["floor_calls"] = np.array(repr(CALLS))
     out["floor_source"] = np.array(body)
 
+    # ---- fusion: the body of DataProcessor's frame loop (preprocessing/data.py:41-61), exec'd verbatim
+    from preprocessing import data as ref_data        # (only for its module-level imports to resolve as in the reference)
+    del ref_data
+    src_lines = open(os.path.join(REF, "preprocessing", "data.py")).read().splitlines()
+    first = next(i for i, ln in enumerate(src_lines) if "registered_pcd_points, registered_pcd_colors = [], []" in ln)
+    last = next(i for i, ln in enumerate(src_lines) if "registered_pcd = filter_outliers(registered_pcd)" in ln)
+    body = "\n".join(ln[12:] if ln.startswith(" " * 12) else ln.strip() for ln in src_lines[first:last + 1])
+    clouds = [scene(3000, 10 + s) for s in range(3)]
+    Ts = [synth.perturbed_extrinsic(np.eye(4), angle_deg=20.0 * (s + 1), shift_mm=(300, -100, 200), unit_scale=1e-3) for s in range(2)]
+    pcs = [PointCloud(c) for c in clouds]
+    for pc in pcs:
+        pc.colors = np.full((len(pc.points), 3), 0.5)
+    ns = {"np": np, "o3d": sys.modules["open3d"], "filter_outliers": ref_filtering.filter_outliers, "filtered_pcds": pcs,
+          "self": types.SimpleNamespace(registration_transformations=Ts)}
+    del CALLS[:]
+    exec(body, ns)
+    out["fuse_in"] = np.stack(clouds)
+    out["fuse_T"] = np.stack(Ts)
+    out["fuse_out"] = np.asarray(ns["registered_pcd"].points, np.float32)
+    out["fuse_calls"] = np.array(repr(CALLS))
+    out["fuse_source"] = np.array(body)
+
+    # ---- utils.processing.statistical_outlier_removal (utils/processing.py:302-310): hard-coded 0.02 voxel
+    from utils import processing as ref_processing
+    so_in = scene(5000, 20)
+    del CALLS[:]
+    got = ref_processing.statistical_outlier_removal(PointCloud(so_in))
+    out["so_in"], out["so_out"] = so_in, np.asarray(got.points, np.float32)
+    out["so_calls"] = np.array(repr(CALLS))
+
     np.savez_compressed(OUT, **out)
-    for k in ("fo_calls", "fo_default_calls", "reg_calls", "floor_calls"):
+    for k in ("fo_calls", "fo_default_calls", "reg_calls", "floor_calls", "fuse_calls", "so_calls"):
         print(k, out[k])
     print("wrote", OUT, {k: getattr(v, "shape", None) for k, v in out.items()})
 

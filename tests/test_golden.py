@@ -157,3 +157,28 @@ def test_mirror_wrappers_make_the_reference_wrappers_calls(oracle, monkeypatch):
     tgt_d = oracle.voxel_downsample(g["reg_master"], 35.0)["points"]
     res = oracle.icp_point_to_plane(src_d, tgt_d, oracle.estimate_normals(tgt_d, 70.0, 40), 100.0, init=g["reg_init"], max_iter=30)
     assert np.array_equal(res["T"], g["reg_T"])
+
+
+def test_mirror_fusion_and_processing_wrappers_make_the_reference_calls(oracle):
+    """``fuse_and_filter`` (the frame-loop body of preprocessing/data.py:41-61) and
+    ``utils.processing.statistical_outlier_removal`` (:302-310): our mirrors against the same stand-in as the
+    reference's code -- master untouched, sub i transformed in place by transformation i-1, device order kept,
+    filter_outliers with its defaults; same results, same calls."""
+    mod = _oracle_backed()
+    PointCloud, _, _ = mod.oracle_backed_namespace()
+    from kinectpy_b200.preprocessing import data as our_data
+    from kinectpy_b200.utils import processing as our_processing
+    g = _compositions()
+    clouds = [PointCloud(c) for c in g["fuse_in"]]
+    del mod.CALLS[:]
+    got = our_data.fuse_and_filter(clouds, list(g["fuse_T"]))
+    assert np.array_equal(np.asarray(got.points, np.float32), g["fuse_out"])
+    assert repr(mod.CALLS) == str(g["fuse_calls"])
+    assert np.array_equal(np.asarray(clouds[0].points, np.float32), g["fuse_in"][0])          # master is not transformed
+    assert not np.array_equal(np.asarray(clouds[1].points, np.float32), g["fuse_in"][1])      # subs are, in place (data.py:48)
+    # the same composition on arrays (what K1 + filter_outliers compute in the frame pipeline)
+    fused = np.concatenate([g["fuse_in"][0]] + [oracle.transform(g["fuse_in"][i], g["fuse_T"][i - 1]) for i in (1, 2)], axis=0)
+    assert np.array_equal(oracle.filter_outliers(fused), g["fuse_out"])
+    del mod.CALLS[:]
+    got = our_processing.statistical_outlier_removal(PointCloud(g["so_in"]))
+    assert np.array_equal(np.asarray(got.points, np.float32), g["so_out"]) and repr(mod.CALLS) == str(g["so_calls"])
