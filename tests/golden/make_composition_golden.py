@@ -13,6 +13,8 @@ copied and what is returned:
 * the floor-removal body of ``floor_removal.py`` (:63-73), exec'd verbatim from the file's own source lines
 * the fusion body of ``DataProcessor``'s frame loop (preprocessing/data.py:41-61), exec'd verbatim likewise
 * ``utils.processing.statistical_outlier_removal``                    (utils/processing.py:302-310)
+* ``preprocessing.registration.execute_global_registration``         (preprocessing/registration.py:32-62)
+* ``preprocessing.registration.execute_colored_ICP_registration``    (preprocessing/registration.py:89-114)
 
 tests/test_golden.py then checks that the oracle's array-level compositions (``oracle.filter_outliers``,
 ``oracle.remove_floor``, and the registration composition the frame pipeline uses) reproduce these outputs;
@@ -53,8 +55,12 @@ def oracle_backed_namespace():
 
         def voxel_down_sample(self, voxel_size):
             CALLS.append(("voxel_down_sample", float(voxel_size), len(self.points)))
-            v = orc.voxel_downsample(self.points, float(voxel_size))
-            return PointCloud(v["points"])
+            has_c = len(self.colors) == len(self.points) and len(self.points) > 0
+            v = orc.voxel_downsample(self.points, float(voxel_size), colors=self.colors if has_c else None)
+            out = PointCloud(v["points"])
+            if has_c:
+                out.colors = v["colors"].astype(np.float64)
+            return out
 
         def remove_statistical_outlier(self, nb_neighbors, std_ratio):
             CALLS.append(("remove_statistical_outlier", int(nb_neighbors), float(std_ratio), len(self.points)))
@@ -109,12 +115,79 @@ def oracle_backed_namespace():
         out.transformation, out.fitness, out.inlier_rmse = r["T"], r["fitness"], r["rmse"]
         return out
 
+    class Feature:
+        def __init__(self, rows):
+            self.rows = rows                    # [n, 33]
+            self.data = rows.T                  # Open3D's layout
+
     def compute_fpfh_feature(pcd, search_param):
         CALLS.append(("compute_fpfh_feature", float(search_param.radius), int(search_param.max_nn), len(pcd.points)))
-        return None             # not consumed by the point-to-plane refinement
+        return Feature(orc.fpfh(pcd.points, pcd.normals, float(search_param.radius), int(search_param.max_nn)))
 
-    registration = types.SimpleNamespace(registration_icp=registration_icp, TransformationEstimationPointToPlane=PointToPlane,
-                                         compute_fpfh_feature=compute_fpfh_feature)
+    class PointToPoint:
+        def __init__(self, with_scaling=False):
+            self.with_scaling = with_scaling
+
+    class EdgeLength:
+        def __init__(self, similarity_threshold=0.9):
+            self.similarity_threshold = similarity_threshold
+
+    class Distance:
+        def __init__(self, distance_threshold):
+            self.distance_threshold = distance_threshold
+
+    class RansacCriteria:
+        def __init__(self, max_iteration=100000, confidence=0.999):
+            self.max_iteration, self.confidence = max_iteration, confidence
+
+    class IcpCriteria:
+        def __init__(self, relative_fitness=1e-6, relative_rmse=1e-6, max_iteration=30):
+            self.relative_fitness, self.relative_rmse, self.max_iteration = relative_fitness, relative_rmse, max_iteration
+
+    class ColoredIcp:
+        pass
+
+    ransac_calls = [0]
+
+    def registration_ransac_based_on_feature_matching(source, target, sf, tf, mutual_filter, max_corr, estimation, ransac_n,
+                                                      checkers, criteria):
+        assert isinstance(estimation, PointToPoint) and estimation.with_scaling is False
+        assert isinstance(checkers[0], EdgeLength) and isinstance(checkers[1], Distance)
+        CALLS.append(("registration_ransac_based_on_feature_matching", bool(mutual_filter), float(max_corr), int(ransac_n),
+                      float(checkers[0].similarity_threshold), float(checkers[1].distance_threshold),
+                      int(criteria.max_iteration), float(criteria.confidence), len(source.points), len(target.points)))
+        nn_st, _ = orc.feature_match(sf.rows, tf.rows)
+        nn_ts, _ = orc.feature_match(tf.rows, sf.rows)
+        cor = orc.mutual_correspondences(nn_st, nn_ts, bool(mutual_filter), int(ransac_n))
+        # successive calls draw from successive streams, as successive upstream calls advance the global generator
+        seed = (1234 + 0x9E3779B97F4A7C15 * ransac_calls[0]) & 0xFFFFFFFFFFFFFFFF
+        ransac_calls[0] += 1
+        r = orc.ransac_correspondence(source.points, target.points, cor, float(max_corr), int(ransac_n),
+                                      float(checkers[0].similarity_threshold), float(checkers[1].distance_threshold),
+                                      int(criteria.max_iteration), float(criteria.confidence), seed=seed)
+        out = Result()
+        out.transformation, out.fitness, out.inlier_rmse = r["T"], r["fitness"], r["rmse"]
+        return out
+
+    def registration_colored_icp(source, target, max_corr, init, estimation, criteria):
+        assert isinstance(estimation, ColoredIcp) and target.has_normals()
+        CALLS.append(("registration_colored_icp", float(max_corr), int(criteria.max_iteration), float(criteria.relative_fitness),
+                      float(criteria.relative_rmse), len(source.points), len(target.points)))
+        r = orc.icp_colored(source.points, source.colors, target.points, target.colors, target.normals, float(max_corr),
+                            init=init, max_iter=int(criteria.max_iteration), rel_fit=float(criteria.relative_fitness),
+                            rel_rmse=float(criteria.relative_rmse))
+        out = Result()
+        out.transformation, out.fitness, out.inlier_rmse = r["T"], r["fitness"], r["rmse"]
+        return out
+
+    registration = types.SimpleNamespace(
+        registration_icp=registration_icp, TransformationEstimationPointToPlane=PointToPlane,
+        compute_fpfh_feature=compute_fpfh_feature, TransformationEstimationPointToPoint=PointToPoint,
+        CorrespondenceCheckerBasedOnEdgeLength=EdgeLength, CorrespondenceCheckerBasedOnDistance=Distance,
+        RANSACConvergenceCriteria=RansacCriteria, ICPConvergenceCriteria=IcpCriteria,
+        TransformationEstimationForColoredICP=ColoredIcp,
+        registration_ransac_based_on_feature_matching=registration_ransac_based_on_feature_matching,
+        registration_colored_icp=registration_colored_icp, _ransac_calls=ransac_calls)
     geometry = types.SimpleNamespace(PointCloud=PointCloud, KDTreeSearchParamHybrid=Hybrid)
     return PointCloud, registration, geometry
 
@@ -227,8 +300,32 @@ def main():
     out["so_in"], out["so_out"] = so_in, np.asarray(got.points, np.float32)
     out["so_calls"] = np.array(repr(CALLS))
 
+    # ---- execute_global_registration (registration.py:32-62): 15 trials, each re-running prepare_dataset
+    reg_ns = sys.modules["open3d"].pipelines.registration
+    gm = scene(3000, 30, mm=True)
+    Dg = synth.perturbed_extrinsic(np.eye(4), angle_deg=25.0, shift_mm=(300, -150, 200), unit_scale=1.0)
+    gs = orc.transform(gm, np.linalg.inv(Dg))
+    del CALLS[:]
+    reg_ns._ransac_calls[0] = 0
+    Tg = ref_registration.execute_global_registration(PointCloud(gm), PointCloud(gs), voxel_size=60, ransac_n_trials=3)
+    out["glob_master"], out["glob_sub"], out["glob_T"] = gm, gs, np.asarray(Tg, np.float64)
+    out["glob_calls"] = np.array(repr(CALLS))
+    assert np.abs(out["glob_T"] - Dg)[:3, :3].max() < 0.05, "the planted transform is recovered"
+
+    # ---- execute_colored_ICP_registration (registration.py:89-114): three scales, each from the initial transform
+    cm = scene(6000, 31, mm=True)
+    ccol = (0.5 + 0.5 * np.sin(cm / 90.0)).astype(np.float32)          # a smooth texture
+    Dc = synth.perturbed_extrinsic(np.eye(4), angle_deg=0.8, shift_mm=(10, -6, 8), unit_scale=1.0)
+    cs = orc.transform(cm, np.linalg.inv(Dc))
+    pm, ps = PointCloud(cm), PointCloud(cs)
+    pm.colors, ps.colors = ccol.astype(np.float64), ccol.astype(np.float64)
+    del CALLS[:]
+    Tc = ref_registration.execute_colored_ICP_registration(pm, ps, np.eye(4))
+    out["col_master"], out["col_sub"], out["col_colors"], out["col_T"] = cm, cs, ccol, np.asarray(Tc, np.float64)
+    out["col_calls"] = np.array(repr(CALLS))
+
     np.savez_compressed(OUT, **out)
-    for k in ("fo_calls", "fo_default_calls", "reg_calls", "floor_calls", "fuse_calls", "so_calls"):
+    for k in ("fo_calls", "fo_default_calls", "reg_calls", "floor_calls", "fuse_calls", "so_calls", "glob_calls", "col_calls"):
         print(k, out[k])
     print("wrote", OUT, {k: getattr(v, "shape", None) for k, v in out.items()})
 

@@ -182,3 +182,36 @@ def test_mirror_fusion_and_processing_wrappers_make_the_reference_calls(oracle):
     del mod.CALLS[:]
     got = our_processing.statistical_outlier_removal(PointCloud(g["so_in"]))
     assert np.array_equal(np.asarray(got.points, np.float32), g["so_out"]) and repr(mod.CALLS) == str(g["so_calls"])
+
+
+def test_mirror_global_and_colored_registration_make_the_reference_calls(oracle, monkeypatch):
+    """``execute_global_registration`` (registration.py:32-62) and ``execute_colored_ICP_registration`` (:89-114): our
+    mirrors against the same oracle-backed stand-in as the reference's code.  Same transforms; same RANSAC / coloured-ICP
+    calls with the same arguments, in the same order.  One documented difference: the reference re-runs the
+    (deterministic) ``prepare_dataset`` in every RANSAC trial, the mirror runs it once."""
+    mod = _oracle_backed()
+    PointCloud, registration, geometry = mod.oracle_backed_namespace()
+    from kinectpy_b200.preprocessing import registration as our_registration
+    g = _compositions()
+    ns = type("G", (), {})()
+    for k, v in list(vars(registration).items()) + list(vars(geometry).items()):
+        setattr(ns, k, v)
+    monkeypatch.setattr(our_registration, "_g", ns)
+    # global registration
+    del mod.CALLS[:]
+    registration._ransac_calls[0] = 0
+    T = our_registration.execute_global_registration(PointCloud(g["glob_master"]), PointCloud(g["glob_sub"]), voxel_size=60,
+                                                     ransac_n_trials=3)
+    assert np.array_equal(np.asarray(T, np.float64), g["glob_T"])
+    ref_calls = eval(str(g["glob_calls"]))
+    is_ransac = lambda c: c[0] == "registration_ransac_based_on_feature_matching"
+    assert [c for c in mod.CALLS if is_ransac(c)] == [c for c in ref_calls if is_ransac(c)] and sum(map(is_ransac, ref_calls)) == 3
+    prep = [c for c in ref_calls if not is_ransac(c)]
+    assert [c for c in mod.CALLS if not is_ransac(c)] == prep[:len(prep) // 3] and prep[:len(prep) // 3] * 3 == prep
+    # coloured ICP: source <- master, target <- sub, every scale from the initial transform, the last scale returned
+    pm, ps = PointCloud(g["col_master"]), PointCloud(g["col_sub"])
+    pm.colors = g["col_colors"].astype(np.float64)
+    ps.colors = g["col_colors"].astype(np.float64)
+    del mod.CALLS[:]
+    T = our_registration.execute_colored_ICP_registration(pm, ps, np.eye(4))
+    assert np.array_equal(np.asarray(T, np.float64), g["col_T"]) and repr(mod.CALLS) == str(g["col_calls"])
