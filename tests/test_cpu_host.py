@@ -185,3 +185,14 @@ def test_bench_reference_arm_line_contract():
     assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_bench_b200_arm_fails_loudly_without_a_gpu():
+    """No silent CPU fallback in the measured arm either: without a CUDA device `bench.py` exits non-zero and says why
+    (the CPU arm is a separate, explicitly requested `--impl reference`)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is visible")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0
+    assert "no CUDA device" in (r.stderr + r.stdout) and not any(ln.startswith("{") for ln in r.stdout.splitlines())
