@@ -228,6 +228,49 @@ def test_ransac_plane(oracle):
         oracle.ransac_plane(pts[:2], 0.01, 3, 10)
 
 
+def test_ransac_plane_vs_independent_numpy_replay(oracle):
+    """segment_plane written out independently in NumPy over the SAME counter-based samples: per-hypothesis plane
+    (normalised cross product), strict-threshold inlier counts and rmse, upstream's sequential best rule with its
+    early-exit bound, final inliers from the winning hypothesis, least-squares refit over them."""
+    r = np.random.default_rng(12)
+    n, H, thr, seed = 4000, 300, 0.01, 77
+    pts = np.stack([r.uniform(-2, 2, n), 1.2 + r.normal(0, 0.003, n), r.uniform(0, 4, n)], axis=1)
+    pts[:1500] = r.uniform(-2, 2, (1500, 3))
+    pts = pts.astype(np.float32)
+    plane, mask, best, counts = oracle.ransac_plane(pts, thr, 3, H, seed=seed)
+    P = pts.astype(np.float64)
+    cnt, rmse, planes = np.zeros(H, np.int64), np.zeros(H), np.zeros((H, 4))
+    for h in range(H):
+        p0, p1, p2 = P[oracle.ransac_sample(seed, h, n, 3)]
+        nn = np.cross(p1 - p0, p2 - p0)
+        if np.linalg.norm(nn) == 0:
+            continue
+        nn /= np.linalg.norm(nn)
+        planes[h] = [*nn, -nn @ p0]
+        e = np.abs(P @ nn - nn @ p0)
+        cnt[h] = (e < thr).sum()
+        rmse[h] = np.sqrt((e[e < thr] ** 2).sum() / max(cnt[h], 1))
+    assert np.array_equal(cnt, counts)
+    bf, br, bi, brk = 0.0, 0.0, -1, float(H)
+    for h in range(H):
+        if h >= brk:
+            continue
+        f = cnt[h] / n
+        if cnt[h] and (f > bf or (f == bf and rmse[h] < br)):
+            bf, br, bi = f, rmse[h], h
+            brk = min(np.log(1 - 0.99999999) / np.log(1 - f ** 3), H) if f < 1 else 0
+    assert bi == best and brk < H                        # the early exit was active in this case
+    inl = np.abs(P @ planes[bi, :3] + planes[bi, 3]) < thr
+    assert np.array_equal(inl, mask.astype(bool))
+    q = P[inl]
+    c = q.mean(0)
+    _, _, Vt = np.linalg.svd(q - c)
+    refit = np.array([*Vt[2], -Vt[2] @ c])
+    if refit[:3] @ plane[:3] < 0:
+        refit = -refit
+    assert np.abs(refit - plane).max() < 1e-5            # upstream's determinant-based fit vs total least squares
+
+
 def test_icp_recovers_planted_transform(oracle):
     from kinectpy_b200 import synth
     tgt = make_surface_cloud(6000, seed=13, outliers=0.0)
