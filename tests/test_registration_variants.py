@@ -63,6 +63,41 @@ def test_oracle_point_to_point_icp_recovers_planted_transform(oracle):
     assert np.array_equal(r0["T"], D) and r0["iters"] == 0
 
 
+def test_oracle_point_to_point_icp_vs_independent_numpy_restatement(oracle):
+    """RegistrationICP + TransformationEstimationPointToPoint(False) written out independently (cKDTree 1-NN inside
+    max_corr, Kabsch by numpy SVD on the matched pairs, T <- U T, relative fitness / rmse stop): same iteration count
+    and fitness as the oracle, transforms equal to rounding."""
+    from conftest import make_surface_cloud
+    from scipy.spatial import cKDTree
+    tgt = make_surface_cloud(5000, seed=23, outliers=0.0)
+    D = synth.perturbed_extrinsic(np.eye(4), angle_deg=0.6, shift_mm=(3, -4, 5), unit_scale=1e-3)
+    src = oracle.transform(tgt[1::2], np.linalg.inv(D))
+    max_corr, max_iter = 0.04, 40
+    res = oracle.icp_point_to_point(src, tgt, max_corr, init=np.eye(4), max_iter=max_iter)
+    tree = cKDTree(tgt.astype(np.float64))
+    T, cur = np.eye(4), src.astype(np.float64)
+
+    def match(p):
+        d, j = tree.query(p, k=1, distance_upper_bound=max_corr)
+        ok = np.isfinite(d) & (d < max_corr)
+        return ok, j, ok.mean(), np.sqrt((d[ok] ** 2).mean())
+
+    ok, j, fit, rmse = match(cur)
+    iters = 0
+    for it in range(max_iter):
+        U = kabsch_numpy(cur[ok], tgt[j[ok]].astype(np.float64))
+        T = U @ T
+        cur = cur @ U[:3, :3].T + U[:3, 3]
+        ok, j, nfit, nrmse = match(cur)
+        iters = it + 1
+        done = abs(fit - nfit) < 1e-6 and abs(rmse - nrmse) < 1e-6
+        fit, rmse = nfit, nrmse
+        if done:
+            break
+    assert res["iters"] == iters and abs(res["fitness"] - fit) < 1e-12 and abs(res["rmse"] - rmse) < 1e-9
+    assert np.abs(res["T"] - T).max() < 1e-9
+
+
 def test_oracle_color_gradient_of_a_linear_ramp(oracle):
     # on the plane z = 0 with intensity a x + b y the tangent-plane gradient is (a, b, 0) everywhere
     r = np.random.default_rng(3)
