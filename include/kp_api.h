@@ -287,11 +287,14 @@ KP_EXPORT int kp_resample_batch(kp_ctx *ctx, const float *d_xyz, const int64_t *
                                 int64_t *h_counts);
 
 /* ------------------------------------------------ whole-frame driver --- */
-/* Batched driver for BASELINE config C4: per frame unproject -> transform ->
- * fuse -> voxel -> SOR -> floor removal (band + RANSAC + merge + SOR) ->
- * ICP refinement of every sub extrinsic (the per-frame body of
+/* Batched, device-driven driver for BASELINE config C4: per frame unproject ->
+ * transform -> fuse -> voxel -> SOR -> floor removal (band + RANSAC + merge +
+ * SOR) -> ICP refinement of every sub extrinsic (the per-frame body of
  * preprocessing/data.py:35-69 followed by floor_removal.py:57-73 and
- * preprocessing/registration.py:65-86). */
+ * preprocessing/registration.py:65-86).  Frames are processed in batches of B
+ * frames per kernel launch; every intermediate count stays on the device, so a
+ * batch is one static launch sequence (a CUDA graph) issued by ONE host thread
+ * with no host round trip; W batch slots are in flight at a time. */
 typedef struct kp_pipeline kp_pipeline;
 typedef struct {
     int32_t S;              /* sensors, sensor 0 = master */
@@ -305,7 +308,7 @@ typedef struct {
     int32_t do_icp;         double icp_voxel; double icp_max_corr; int32_t icp_max_iter;
     int32_t normals_max_nn; double normals_radius;
     uint64_t seed;
-    int32_t n_streams;      /* frames in flight (worker threads, one ctx each) */
+    int32_t n_streams;      /* frames in flight = B frames per launch x W batch slots (no worker threads) */
 } kp_pipeline_cfg;
 typedef struct {
     int64_t n_fused, n_voxel, n_sor, n_floor_inliers, n_out;
@@ -321,14 +324,19 @@ KP_EXPORT const char *kp_pipeline_last_error(kp_pipeline *p);
 /* depth uint16 [F][S][P]; depth_on_device != 0 -> device pointer (value leg),
  * else host pointer (e2e leg: H2D inside).  h_results [F].  d_out_xyz nullable
  * float32 [F][out_stride][3] device buffer receiving each frame's final cloud
- * (rows beyond n_out are left untouched). */
+ * (rows beyond n_out are left untouched).  A frame whose final cloud has more
+ * than out_stride rows is copied up to out_stride rows, its status and the
+ * call's return value are KP_E_RANGE. */
 KP_EXPORT int kp_pipeline_run(kp_pipeline *p, const uint16_t *depth, int depth_on_device, int64_t F,
                               kp_frame_result *h_results, float *d_out_xyz, int64_t out_stride);
-/* e2e form: as kp_pipeline_run with host depth, and each frame's final cloud is also copied to the
- * (pinned) host buffer h_out_xyz float32 [F][out_stride][3] (first n_out rows of each frame). */
+/* e2e form: as kp_pipeline_run with host depth, and each frame's final cloud is written to the
+ * PINNED host buffer (kp_host_alloc) h_out_xyz float32 [F][out_stride][3] (first n_out rows of each
+ * frame) by a device kernel: the row counts never visit the host before the copy. */
 KP_EXPORT int kp_pipeline_run_host(kp_pipeline *p, const uint16_t *h_depth, int64_t F, kp_frame_result *h_results,
                                    float *h_out_xyz, int64_t out_stride);
 KP_EXPORT int64_t kp_pipeline_launch_count(kp_pipeline *p);
+/* frames per launch (B) and batch slots in flight (W) the pipeline was built with */
+KP_EXPORT int kp_pipeline_frames_in_flight(kp_pipeline *p, int *batch, int *slots);
 KP_EXPORT int kp_pipeline_profile(kp_pipeline *p, int enable_or_read, int max_entries,
                                   const char **h_names, double *h_ms, int64_t *h_calls, double *h_bytes, int *h_n);
 

@@ -14,7 +14,10 @@
 // shell of cells is probed (isolated outliers -- the points SOR exists to find -- take this path).
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
+#include <vector>
 #include "kp_grid.cuh"
+#include "kp_batch.cuh"
 
 KpGridDev kp_grid_dev(const KpGrid &g)
 {
@@ -266,7 +269,29 @@ struct KnnParams {
     uint8_t *strag_flags;                          // thread kernel: flags[q] = 1 for queries it could not certify
     const float4 *qpts;                            // self-query source rows (level-0 cell-sorted array)
     int32_t *dbg;                                  // optional [8] tally of the reasons level 1 hands a query on (KP_DEBUG_KNN)
+    // frame engine (batched launches, kp_engine.cu): the grid layout and the query count were produced on the device
+    const KpGridDev *gdev;                         // non-NULL: replaces g
+    const int32_t *nq_dev;                         // non-NULL: replaces nq
 };
+
+// batched launches read their parameter block from device memory (blockIdx.y selects the frame): the block is
+// copied to shared memory once per CTA and the device-side grid layout / query count are patched in
+__device__ __forceinline__ const KnnParams &knn_params_batched(const KnnParams *pp)
+{
+    __shared__ KnnParams s_p;
+    const int *src = reinterpret_cast<const int *>(pp + blockIdx.y);
+    int *dst = reinterpret_cast<int *>(&s_p);
+    for (int i = threadIdx.x; i < (int)(sizeof(KnnParams) / 4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    if (s_p.gdev) {
+        const int *gs = reinterpret_cast<const int *>(s_p.gdev);
+        int *gd = reinterpret_cast<int *>(&s_p.g);
+        for (int i = threadIdx.x; i < (int)(sizeof(KpGridDev) / 4); i += blockDim.x) gd[i] = gs[i];
+    }
+    if (threadIdx.x == 0 && s_p.nq_dev) s_p.nq = *s_p.nq_dev;
+    __syncthreads();
+    return s_p;
+}
 
 __device__ __forceinline__ bool kq_less(double d, int i, double td, int ti) { return d < td || (d == td && i < ti); }
 
@@ -553,9 +578,8 @@ __device__ void kq_finalize(const KnnParams &p, int64_t row, int cnt, const doub
 
 // ---- warp-per-query kernel: any k, ring expansion, linear-scan fallback.  Used for large k, for external
 // queries and for the stragglers the thread-per-query kernel hands over (qlist / qcount).
-__global__ void __launch_bounds__(KQ_WARPS * 32) k_knn(const __grid_constant__ KnnParams p)
+__device__ __forceinline__ void knn_warp_body(const KnnParams &p, unsigned char *smem_raw)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const KpGridDev &g = p.g;
     const int64_t nq = p.qcount ? (int64_t)*p.qcount : p.nq;
@@ -661,6 +685,16 @@ __global__ void __launch_bounds__(KQ_WARPS * 32) k_knn(const __grid_constant__ K
         }
         __syncwarp();
     }
+}
+__global__ void __launch_bounds__(KQ_WARPS * 32) k_knn(const __grid_constant__ KnnParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    knn_warp_body(p, smem_raw);
+}
+__global__ void __launch_bounds__(KQ_WARPS * 32) k_knn_b(const KnnParams *pp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    knn_warp_body(knn_params_batched(pp), smem_raw);
 }
 
 // ---- histogram-select kernels (the fast path: k <= HQ_KMAX, the cloud queries itself).
@@ -773,14 +807,10 @@ __device__ void kq_finish_normal(const KnnParams &p, int64_t row, int cnt, doubl
 }
 
 template <int NB, int R, int HQT>
-__global__ void __launch_bounds__(HQT) k_knn_hist(const __grid_constant__ KnnParams p)
+__device__ __forceinline__ void hq_query(const KnnParams &p, const int64_t q, unsigned char *smem_raw)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const KpGridDev &g = p.g;
     const int tid = threadIdx.x;
-    const int64_t w = (int64_t)blockIdx.x * HQT + tid;
-    if (w >= p.nq) return;
-    const int64_t q = w;
     // buf[slot * HQT], hist[bin * HQT]: any slot pattern is bank-conflict free
     unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem_raw) + tid;
     unsigned short *hist = reinterpret_cast<unsigned short *>(smem_raw + (size_t)p.cap * HQT * sizeof(unsigned long long)) + tid;
@@ -961,6 +991,21 @@ __global__ void __launch_bounds__(HQT) k_knn_hist(const __grid_constant__ KnnPar
     if (p.count) p.count[row] = cnt;
     if (p.mean) p.mean[row] = cnt > 0 ? __ddiv_rn(acc, (double)cnt) : -1.0;
 }
+template <int NB, int R, int HQT>
+__global__ void __launch_bounds__(HQT) k_knn_hist(const __grid_constant__ KnnParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int64_t w = (int64_t)blockIdx.x * HQT + threadIdx.x;
+    if (w >= p.nq) return;
+    hq_query<NB, R, HQT>(p, w, smem_raw);
+}
+template <int NB, int R, int HQT>
+__global__ void __launch_bounds__(HQT) k_knn_hist_b(const KnnParams *pp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const KnnParams &p = knn_params_batched(pp);
+    for (int64_t w = (int64_t)blockIdx.x * HQT + threadIdx.x; w < p.nq; w += (int64_t)gridDim.x * HQT) hq_query<NB, R, HQT>(p, w, smem_raw);
+}
 
 // ---- warp-per-query best-first histogram select: the level-0 stragglers (isolated points and sparse fringes
 // -- what SOR is looking for) against a coarser grid.  Their k-th neighbour can be a metre away, so the block
@@ -1058,7 +1103,7 @@ __device__ __forceinline__ int wh_select(const unsigned int *hist, int k, int la
     return bb;
 }
 
-__global__ void __launch_bounds__(WH_WARPS * 32) k_knn_wbf(const __grid_constant__ KnnParams p)
+__device__ __forceinline__ void knn_wbf_body(const KnnParams &p)
 {
     __shared__ unsigned int s_hist[WH_WARPS][WH_NB];
     __shared__ unsigned long long s_buf[WH_WARPS][WH_CAP];
@@ -1199,6 +1244,8 @@ __global__ void __launch_bounds__(WH_WARPS * 32) k_knn_wbf(const __grid_constant
         __syncwarp();
     }
 }
+__global__ void __launch_bounds__(WH_WARPS * 32) k_knn_wbf(const __grid_constant__ KnnParams p) { knn_wbf_body(p); }
+__global__ void __launch_bounds__(WH_WARPS * 32) k_knn_wbf_b(const KnnParams *pp) { knn_wbf_body(knn_params_batched(pp)); }
 
 int next_pow2(int v)
 {
@@ -1257,6 +1304,7 @@ int knn_launch(kp_ctx *ctx, KnnParams &p, const char *name, const float *d_xyz =
                    : (p.idx ? 4.0 * p.k : 0.0) + (p.d2 ? 8.0 * p.k : 0.0) + (p.count ? 4.0 : 0.0) + (p.mean ? 8.0 : 0.0);
     KP_PROFB(ctx, name, (double)p.g.npts * 16.0 + (double)p.nq * (out_b + (p.queries ? 12.0 : 0.0)));
     p.qlist = nullptr; p.qcount = nullptr; p.strag_flags = nullptr; p.dbg = nullptr;
+    p.gdev = nullptr; p.nq_dev = nullptr;
     p.qpts = p.g.pts;
     const bool fast = !p.queries && p.mode != KQ_MODE_RADIUS && p.k <= HQ_KMAX;
     if (!fast) return knn_launch_warp(ctx, p, p.nq);
@@ -1439,6 +1487,93 @@ int kp_normals_device(kp_ctx *ctx, const float *d_xyz, int64_t n, double radius,
     p.idx = nullptr; p.d2 = nullptr; p.count = nullptr; p.mean = nullptr;
     p.cloud = d_xyz; p.normals = d_normals; p.rcount = nullptr;
     return knn_launch(ctx, p, "normals");
+}
+
+// ---------------------------------------------------------------- frame engine: batched neighbour searches
+// One parameter block per (level, segment) lives in device memory, written once when the engine is created
+// (every pointer in it is static; grid layouts and counts are read through gdev / nq_dev / qcount at run time).
+int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, int mode, double radius, KpKnnBatch *out)
+{
+    out->nseg = nseg; out->k = k; out->mode = mode;
+    static const int slack = getenv("KP_KNN_SLACK") ? atoi(getenv("KP_KNN_SLACK")) : 8;
+    out->cap_hist = k + slack;
+    int capw = next_pow2(4 * k > 128 ? 4 * k : 128);
+    if ((size_t)KQ_WARPS * capw * 12 > 96 * 1024) capw = next_pow2(k + 64 > 128 ? k + 64 : 128);
+    out->cap_warp = capw;
+    if (k > HQ_KMAX) return kp_set_err(ctx, KP_E_ARG, "frame engine: k = %d neighbours exceeds the histogram kernel's %d", k, HQ_KMAX);
+    std::vector<KnnParams> h((size_t)3 * nseg);
+    for (int s = 0; s < nseg; ++s) {
+        const KpKnnSegDesc &d = segs[s];
+        KnnParams p;
+        memset(&p, 0, sizeof p);
+        p.queries = nullptr; p.nq = 0; p.k = k; p.mode = mode == 1 ? KQ_MODE_NORMALS : KQ_MODE_KNN; p.rad = 1;
+        p.r2cap = radius > 0 ? radius * radius : 0.0;
+        p.mean = d.mean; p.cloud = d.cloud; p.normals = d.normals;
+        p.qpts = d.pts0;
+        // level 0: every point of the cloud, one thread each, against the level-0 grid
+        KnnParams a = p;
+        a.cap = out->cap_hist; a.gdev = d.g0; a.nq_dev = d.n; a.strag_flags = d.flags0;
+        h[s] = a;
+        // level 1: the level-0 leftovers (list0), one warp each, against the coarse grid
+        KnnParams b = p;
+        b.cap = out->cap_hist; b.gdev = d.g1; b.qlist = d.list0; b.qcount = d.cnt0; b.strag_flags = d.flags1;
+        h[(size_t)nseg + s] = b;
+        // stragglers: ring expansion on the coarse grid
+        KnnParams c = p;
+        c.cap = capw; c.gdev = d.g1; c.qlist = d.list1; c.qcount = d.cnt1;
+        h[(size_t)2 * nseg + s] = c;
+    }
+    KP_CUDA(ctx, cudaMalloc(&out->d_params, sizeof(KnnParams) * h.size()));
+    KP_CUDA(ctx, cudaMemcpy(out->d_params, h.data(), sizeof(KnnParams) * h.size(), cudaMemcpyHostToDevice));
+    // shared-memory opt-ins happen here, not inside a stream capture
+    const size_t smem_w = (size_t)KQ_WARPS * capw * (sizeof(double) + sizeof(int));
+    if (smem_w > 200 * 1024) return kp_set_err(ctx, KP_E_ARG, "k = %d neighbours is too many for the per-warp buffer", k);
+    if (smem_w > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+    const size_t smem_h = (size_t)(k <= 32 ? 128 : 64) * ((size_t)out->cap_hist * 8 + (size_t)(k <= 32 ? 32 : 64) * 2);
+    if (smem_h > 48 * 1024) {
+        if (k <= 32) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist_b<32, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+        else KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist_b<64, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+    }
+    return KP_OK;
+}
+void kp_knn_batch_destroy(KpKnnBatch *b)
+{
+    if (b && b->d_params) { cudaFree(b->d_params); b->d_params = nullptr; }
+}
+int kp_knn_batch_level0(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows)
+{
+    const KnnParams *pp = (const KnnParams *)b.d_params;
+    KP_PROFB(ctx, "knn_level0", 0.0);
+    if (b.k <= 32) {
+        constexpr int T = 128;
+        const size_t smem = (size_t)T * ((size_t)b.cap_hist * 8 + 32 * 2);
+        int64_t gx = (cap_rows + T - 1) / T;
+        if (gx > (int64_t)ctx->sm_count * 24) gx = (int64_t)ctx->sm_count * 24;
+        k_knn_hist_b<32, 1, T><<<dim3((unsigned)(gx > 0 ? gx : 1), (unsigned)b.nseg), T, smem, ctx->stream>>>(pp);
+    } else {
+        constexpr int T = 64;
+        const size_t smem = (size_t)T * ((size_t)b.cap_hist * 8 + 64 * 2);
+        int64_t gx = (cap_rows + T - 1) / T;
+        if (gx > (int64_t)ctx->sm_count * 32) gx = (int64_t)ctx->sm_count * 32;
+        k_knn_hist_b<64, 1, T><<<dim3((unsigned)(gx > 0 ? gx : 1), (unsigned)b.nseg), T, smem, ctx->stream>>>(pp);
+    }
+    KP_LAUNCH_CHECK(ctx);
+    return KP_OK;
+}
+int kp_knn_batch_level1(kp_ctx *ctx, const KpKnnBatch &b)
+{
+    KP_PROFB(ctx, "knn_level1", 0.0);
+    k_knn_wbf_b<<<dim3((unsigned)ctx->sm_count * 8, (unsigned)b.nseg), WH_WARPS * 32, 0, ctx->stream>>>((const KnnParams *)b.d_params + b.nseg);
+    KP_LAUNCH_CHECK(ctx);
+    return KP_OK;
+}
+int kp_knn_batch_stragglers(kp_ctx *ctx, const KpKnnBatch &b)
+{
+    KP_PROFB(ctx, "knn_stragglers", 0.0);
+    const size_t smem = (size_t)KQ_WARPS * b.cap_warp * (sizeof(double) + sizeof(int));
+    k_knn_b<<<dim3((unsigned)ctx->sm_count * 4, (unsigned)b.nseg), KQ_WARPS * 32, smem, ctx->stream>>>((const KnnParams *)b.d_params + 2 * b.nseg);
+    KP_LAUNCH_CHECK(ctx);
+    return KP_OK;
 }
 
 extern "C" {

@@ -15,7 +15,9 @@
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
+#include <vector>
 #include "kp_grid.cuh"
+#include "kp_batch.cuh"
 #include "kp_umeyama.cuh"
 
 namespace {
@@ -39,6 +41,7 @@ struct IcpState {
     int done, iters;
     unsigned int ticket;
     int pass;                   // number of the pass the next launch executes (advanced by the last CTA)
+    double slack;               // frame engine: the fp32 pre-test slack, computed on the device from the grid extent
 };
 
 struct IcpParams {
@@ -60,7 +63,42 @@ struct IcpParams {
     double *slots;              // [gridDim.x][ICP_NV]
     double *gslots;             // [groups][ICP_NV] group rows
     unsigned int *gticket;      // [groups] zero between passes
+    // frame engine (batched launches, blockIdx.y = pair): values produced on the device
+    const KpGridDev *gdev;      // non-NULL: replaces g
+    const int32_t *ns_dev;      // non-NULL: replaces ns
+    const float *src;           // source cloud of the pair
+    double max_corr;
+    double init_T[16];
+    double *res_T, *res_fit, *res_rmse; int32_t *res_iters;   // where the converged state of the pair goes
 };
+
+__device__ __forceinline__ double icp_slack(const KpGridDev &g, double max_corr)
+{
+    // fp32 rounding of a coordinate of magnitude <= M costs <= M * 2^-24 per operand; 8 x that covers the
+    // three axes, both operands and the fp32 arithmetic with room to spare
+    double M = 0.0;
+    for (int c = 0; c < 3; ++c)
+        M = fmax(M, fmax(fabs(g.org[c]), fabs(g.org[c] + g.cell * (double)g.dim[c])) + 2.0 * max_corr);
+    const double eps = 8.0 * M / 16777216.0;          // bound on |sqrt(fp32 d2) - sqrt(d2)|
+    return eps * (2.0 * max_corr + eps) * 1.000001 + 4e-6 * (max_corr * max_corr);
+}
+
+// batched launches: parameter block of pair blockIdx.y from device memory into shared memory, with the device-side
+// grid layout, source count and slack patched in
+__device__ __forceinline__ const IcpParams &icp_params_batched(const IcpParams *pp)
+{
+    __shared__ IcpParams s_p;
+    const int *src = reinterpret_cast<const int *>(pp + blockIdx.y);
+    int *dst = reinterpret_cast<int *>(&s_p);
+    for (int i = threadIdx.x; i < (int)(sizeof(IcpParams) / 4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    const int *gs = reinterpret_cast<const int *>(s_p.gdev);
+    int *gd = reinterpret_cast<int *>(&s_p.g);
+    for (int i = threadIdx.x; i < (int)(sizeof(KpGridDev) / 4); i += blockDim.x) gd[i] = gs[i];
+    if (threadIdx.x == 0) { s_p.ns = *s_p.ns_dev; s_p.slack = s_p.st->slack; }
+    __syncthreads();
+    return s_p;
+}
 
 __global__ void __launch_bounds__(256) k_icp_init(const float *src, int ns, const __grid_constant__ IcpParams p, IcpState init,
                                                   double *out)
@@ -259,7 +297,7 @@ __device__ void icp_finish(const IcpParams &p, IcpState *st, const double *tot, 
 // One pass: update + correspondence + accumulation, one thread per source point; the last CTA solves and
 // publishes the next update.
 template <int MODE>
-__global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __grid_constant__ IcpParams p)
+__device__ __forceinline__ void icp_iter_body(const IcpParams &p)
 {
     __shared__ double sh[ICP_THREADS / 32][ICP_NV];
     __shared__ double part[ICP_THREADS / 32][32];
@@ -383,8 +421,10 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __
     // one CTA walking ~2000 rows; the tickets see ICP_GROUP and gridDim/ICP_GROUP atomics per address instead of
     // gridDim.  Fixed tree -> the sums do not depend on which CTA does the folding.
     constexpr int W = ICP_THREADS / 32;
-    const unsigned group = blockIdx.x / ICP_GROUP, ngroups = (gridDim.x + ICP_GROUP - 1) / ICP_GROUP;
-    const unsigned g0 = group * ICP_GROUP, gsize = min((unsigned)ICP_GROUP, gridDim.x - g0);
+    // (the CTAs that own source points: a batched launch is sized for the capacity and the rest left at once)
+    const unsigned nact = max(1u, ((unsigned)p.ns + ICP_THREADS - 1) / ICP_THREADS);
+    const unsigned group = blockIdx.x / ICP_GROUP, ngroups = (nact + ICP_GROUP - 1) / ICP_GROUP;
+    const unsigned g0 = group * ICP_GROUP, gsize = min((unsigned)ICP_GROUP, nact - g0);
     auto fold = [&](const double *rows, unsigned nrows, double *dst_sh) {
         // warp w adds rows w, w + W, ... (all its loads in flight together), then the W partial sums in order
         double sacc = 0;
@@ -427,7 +467,113 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __
     __syncthreads();
     icp_finish(p, st, tot, pass, tid);
 }
+template <int MODE>
+__global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __grid_constant__ IcpParams p)
+{
+    icp_iter_body<MODE>(p);
+}
+template <int MODE>
+__global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter_b(const IcpParams *pp)
+{
+    // CTAs beyond the pair's source count, and every CTA of a converged pair, leave before touching anything else
+    const IcpParams *me = pp + blockIdx.y;
+    const int ns = *me->ns_dev;
+    if (blockIdx.x * ICP_THREADS >= (unsigned)max(ns, 1) || me->st->done) return;
+    icp_iter_body<MODE>(icp_params_batched(pp));
+}
+// batched init: moving source = init * src, state reset, slack from the device-side grid
+__global__ void __launch_bounds__(256) k_icp_init_b(const IcpParams *pp)
+{
+    const IcpParams *p = pp + blockIdx.y;
+    const int ns = *p->ns_dev;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        IcpState init;
+        memset(&init, 0, sizeof init);
+        for (int i = 0; i < 16; ++i) { init.T[i] = p->init_T[i]; init.U[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+        init.slack = icp_slack(*p->gdev, p->max_corr);
+        *p->st = init;
+    }
+    const double *T = p->init_T;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
+        const double X = p->src[3 * (int64_t)i], Y = p->src[3 * (int64_t)i + 1], Z = p->src[3 * (int64_t)i + 2];
+        p->cur[3 * (int64_t)i] = kp_affine(T[0], T[1], T[2], T[3], X, Y, Z);
+        p->cur[3 * (int64_t)i + 1] = kp_affine(T[4], T[5], T[6], T[7], X, Y, Z);
+        p->cur[3 * (int64_t)i + 2] = kp_affine(T[8], T[9], T[10], T[11], X, Y, Z);
+    }
+}
+__global__ void k_icp_results_b(const IcpParams *pp, int npairs)
+{
+    // one thread per pair: the converged state into the frame's result rows
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    const IcpParams &p = pp[i];
+    const IcpState *st = p.st;
+    for (int e = 0; e < 16; ++e) p.res_T[e] = st->T[e];
+    *p.res_fit = st->fitness; *p.res_rmse = st->rmse; *p.res_iters = st->iters;
+}
 }  // namespace
+
+// ---------------------------------------------------------------- frame engine: batched point-to-plane ICP
+int kp_icp_batch_create(kp_ctx *ctx, const KpIcpPairDesc *pairs, int npairs, int64_t cap_src, double max_corr, int max_iter,
+                        double rel_fitness, double rel_rmse, KpIcpBatch *out)
+{
+    out->npairs = npairs; out->max_iter = max_iter < 0 ? 0 : max_iter; out->cap_src = cap_src;
+    const int grid = (int)kp_blocks(cap_src > 0 ? cap_src : 1, ICP_THREADS);
+    const int ngroups = (grid + ICP_GROUP - 1) / ICP_GROUP;
+    out->grid = grid;
+    const size_t per_pair = (size_t)cap_src * 3 * sizeof(double) + (size_t)cap_src * sizeof(int32_t) + (size_t)grid * ICP_NV * sizeof(double) +
+                            (size_t)ngroups * ICP_NV * sizeof(double) + (size_t)ngroups * sizeof(unsigned int) + sizeof(IcpState) + 1024;
+    KP_CUDA(ctx, cudaMalloc(&out->d_work, per_pair * (size_t)npairs));
+    KP_CUDA(ctx, cudaMemset(out->d_work, 0, per_pair * (size_t)npairs));
+    std::vector<IcpParams> h((size_t)npairs);
+    char *w = (char *)out->d_work;
+    auto take = [&](size_t bytes) { char *r = w; w += (bytes + 255) & ~(size_t)255; return r; };
+    for (int i = 0; i < npairs; ++i) {
+        IcpParams p;
+        memset(&p, 0, sizeof p);
+        p.tgt_normals = pairs[i].tgt_normals; p.mode = ICP_PLANE;
+        p.sqrt_lg = 1.0; p.sqrt_lp = 0.0;
+        p.cur = (double *)take((size_t)cap_src * 3 * sizeof(double));
+        p.corr = (int32_t *)take((size_t)cap_src * sizeof(int32_t));
+        p.slots = (double *)take((size_t)grid * ICP_NV * sizeof(double));
+        p.gslots = (double *)take((size_t)ngroups * ICP_NV * sizeof(double));
+        p.gticket = (unsigned int *)take((size_t)ngroups * sizeof(unsigned int));
+        p.st = (IcpState *)take(sizeof(IcpState));
+        p.r2 = max_corr * max_corr; p.max_corr = max_corr;
+        p.max_iter = out->max_iter; p.rel_fit = rel_fitness; p.rel_rmse = rel_rmse;
+        p.gdev = pairs[i].tgt_grid; p.ns_dev = pairs[i].n_src; p.src = pairs[i].src;
+        for (int e = 0; e < 16; ++e) p.init_T[e] = pairs[i].init_T[e];
+        p.res_T = pairs[i].res_T; p.res_fit = pairs[i].res_fit; p.res_rmse = pairs[i].res_rmse; p.res_iters = pairs[i].res_iters;
+        h[i] = p;
+    }
+    KP_CUDA(ctx, cudaMalloc(&out->d_params, sizeof(IcpParams) * h.size()));
+    KP_CUDA(ctx, cudaMemcpy(out->d_params, h.data(), sizeof(IcpParams) * h.size(), cudaMemcpyHostToDevice));
+    return KP_OK;
+}
+void kp_icp_batch_destroy(KpIcpBatch *b)
+{
+    if (!b) return;
+    if (b->d_params) cudaFree(b->d_params);
+    if (b->d_work) cudaFree(b->d_work);
+    b->d_params = b->d_work = nullptr;
+}
+int kp_icp_batch_run(kp_ctx *ctx, const KpIcpBatch &b)
+{
+    KpProfScope prof_scope__(ctx, "icp");
+    const IcpParams *pp = (const IcpParams *)b.d_params;
+    int64_t gi = (b.cap_src + 255) / 256;
+    if (gi > (int64_t)ctx->sm_count * 8) gi = (int64_t)ctx->sm_count * 8;
+    k_icp_init_b<<<dim3((unsigned)(gi > 0 ? gi : 1), (unsigned)b.npairs), 256, 0, ctx->stream>>>(pp);
+    KP_LAUNCH_CHECK(ctx);
+    for (int i = 0; i <= b.max_iter; ++i) {
+        k_icp_iter_b<ICP_PLANE><<<dim3((unsigned)b.grid, (unsigned)b.npairs), ICP_THREADS, 0, ctx->stream>>>(pp);
+        KP_LAUNCH_CHECK(ctx);
+    }
+    k_icp_results_b<<<kp_blocks(b.npairs, 64), 64, 0, ctx->stream>>>(pp, b.npairs);
+    KP_LAUNCH_CHECK(ctx);
+    return KP_OK;
+}
+
 
 // internal form: the target grid is built by the caller (pipeline reuses it for both subs)
 namespace {
@@ -515,6 +661,7 @@ int kp_icp_device(kp_ctx *ctx, const float *d_src, int64_t n_src, const KpGrid &
     if (max_iter < 0) max_iter = 0;
     KpProfScope prof_scope__(ctx, "icp");
     IcpParams p;
+    memset(&p, 0, sizeof p);
     p.g = kp_grid_dev(tgt_grid);
     if (tgt_grid.n <= 0) p.g.dim[0] = p.g.dim[1] = p.g.dim[2] = 0;
     p.tgt_normals = d_tgt_normals;

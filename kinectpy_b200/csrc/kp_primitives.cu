@@ -3,6 +3,7 @@
 // run-head extraction, bounds, canonical double sums.  No CUB/Thrust on the product path.
 #include <math.h>
 #include "kp_common.cuh"
+#include "kp_batch.cuh"
 
 // ===================================================== ordered compaction ==
 // Tile = 256 threads x 8 items, striped: item j of thread t is element base + j*256 + t, so the
@@ -311,8 +312,12 @@ constexpr int RS_ITEMS = 8;    // 2048-key tiles: enough CTAs to fill 148 SMs al
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
 
 template <class K>
-__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K *keys, int64_t n, int shift, int32_t *g_hist, int nb)
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K *keys, int64_t n, int shift, int32_t *g_hist, int nb,
+                                                        int64_t seg_stride)
 {
+    // blockIdx.y = segment of a batched sort (kp_b_sort_pairs_u32): every array advances by its per-segment stride
+    keys += (int64_t)blockIdx.y * seg_stride;
+    g_hist += (int64_t)blockIdx.y * 256 * nb;
     __shared__ int hist[256];
     hist[threadIdx.x] = 0;
     __syncthreads();
@@ -350,6 +355,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K *keys, int64_t n
 // one block per digit: exclusive scan of that digit's per-tile counts (row of g_hist), total to g_tot[digit]
 __global__ void __launch_bounds__(256) k_rs_scan_rows(int32_t *g_hist, int nb, int32_t *g_tot)
 {
+    g_hist += (int64_t)blockIdx.y * 256 * nb;
+    g_tot += (int64_t)blockIdx.y * 256;
     __shared__ int warp_tot[8];
     const int d = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     int32_t *row = g_hist + (int64_t)d * nb;
@@ -376,8 +383,13 @@ __global__ void __launch_bounds__(256) k_rs_scan_rows(int32_t *g_hist, int nb, i
 template <class K>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K *keys_in, const int32_t *vals_in, K *keys_out,
                                                            int32_t *vals_out, int64_t n, int shift,
-                                                           const int32_t *g_hist, const int32_t *g_tot, int nb)
+                                                           const int32_t *g_hist, const int32_t *g_tot, int nb,
+                                                           int64_t seg_stride)
 {
+    keys_in += (int64_t)blockIdx.y * seg_stride; keys_out += (int64_t)blockIdx.y * seg_stride;
+    if (vals_in) vals_in += (int64_t)blockIdx.y * seg_stride;
+    vals_out += (int64_t)blockIdx.y * seg_stride;
+    g_hist += (int64_t)blockIdx.y * 256 * nb; g_tot += (int64_t)blockIdx.y * 256;
     __shared__ int cnt[RS_WARPS][256];
     __shared__ int dig_wtot[RS_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -468,12 +480,12 @@ int sort_pairs(kp_ctx *ctx, int64_t n, int bits, K *d_keys, K *d_keys_tmp, int32
     int32_t *vin = d_vals, *vout = d_vals_tmp;
     for (int p = 0; p < passes; ++p) {
         int shift = 8 * p;
-        k_rs_hist<K><<<nb, RS_THREADS, 0, ctx->stream>>>(kin, n, shift, g_hist, nb);
+        k_rs_hist<K><<<nb, RS_THREADS, 0, ctx->stream>>>(kin, n, shift, g_hist, nb, 0);
         KP_LAUNCH_CHECK(ctx);
         k_rs_scan_rows<<<256, 256, 0, ctx->stream>>>(g_hist, nb, g_base);
         KP_LAUNCH_CHECK(ctx);
         k_rs_scatter<K><<<nb, RS_THREADS, 0, ctx->stream>>>(kin, (p == 0 && vals_are_iota) ? nullptr : vin, kout, vout, n,
-                                                            shift, g_hist, g_base, nb);
+                                                            shift, g_hist, g_base, nb, 0);
         KP_LAUNCH_CHECK(ctx);
         K *tk = kin; kin = kout; kout = tk;
         int32_t *tv = vin; vin = vout; vout = tv;
@@ -483,6 +495,32 @@ int sort_pairs(kp_ctx *ctx, int64_t n, int bits, K *d_keys, K *d_keys_tmp, int32
     return KP_OK;
 }
 }  // namespace
+
+// batched form (kp_batch.cuh): `nseg` independent sorts of n rows each, one launch per kernel and pass
+size_t kp_b_sort_hist_elems(int64_t n) { return (size_t)256 * kp_blocks(n > 0 ? n : 1, RS_TILE); }
+int kp_b_sort_pairs_u32(const BLaunch &L, const BSort &W, int64_t n, int passes, uint32_t *keys, uint32_t *keys_tmp,
+                        int32_t *vals, int32_t *vals_tmp, int64_t stride)
+{
+    if (n <= 0 || L.nseg <= 0) return KP_OK;
+    kp_ctx *ctx = L.ctx;
+    KP_PROFB(ctx, "radix_sort", (double)L.nseg * (double)n * (passes * 2.0 * 8.0 + 4.0));
+    const int nb = (int)kp_blocks(n, RS_TILE);
+    uint32_t *kin = keys, *kout = keys_tmp;
+    int32_t *vin = vals, *vout = vals_tmp;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = 8 * p;
+        k_rs_hist<uint32_t><<<dim3(nb, L.nseg), RS_THREADS, 0, ctx->stream>>>(kin, n, shift, W.g_hist, nb, stride);
+        KP_LAUNCH_CHECK(ctx);
+        k_rs_scan_rows<<<dim3(256, L.nseg), 256, 0, ctx->stream>>>(W.g_hist, nb, W.g_tot);
+        KP_LAUNCH_CHECK(ctx);
+        k_rs_scatter<uint32_t><<<dim3(nb, L.nseg), RS_THREADS, 0, ctx->stream>>>(kin, p == 0 ? nullptr : vin, kout, vout, n, shift,
+                                                                                 W.g_hist, W.g_tot, nb, stride);
+        KP_LAUNCH_CHECK(ctx);
+        uint32_t *tk = kin; kin = kout; kout = tk;
+        int32_t *tv = vin; vin = vout; vout = tv;
+    }
+    return KP_OK;
+}
 
 // The value of element i entering the first pass is its input position i (iota), synthesised in
 // the scatter kernel instead of being read, so d_vals need not be initialised.

@@ -20,7 +20,10 @@ struct UnprojParams {
     float *xyz;
     uint8_t *valid;
     int16_t *xyz16;
-    int32_t *bounds_enc;   // BOUNDS variants: [B][S][tiles][warps][8] slots of ordered-int min xyz, max xyz, count, pad
+    int32_t *bounds_enc;   // BOUNDS variants: [B][S][sets][tiles][warps][8] slots of ordered-int min xyz, max xyz, count, pad
+    float *xyz_raw;        // RAW variant (frame engine): second output [B][S][P][3] = the same points BEFORE the extrinsic for
+                           // s >= 1 (the ICP sources, in their own sensor frame) and the transformed master for s = 0;
+                           // its bounds go to slot set 1
     double T[UP_MAX_S][12];
 };
 
@@ -31,7 +34,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 // reused for every frame of the batch; depth streams through with one 128-bit load per thread.
 // Compile-time variants (k4a int16 rounding, drop-any-zero rule, extrinsic, bounds) so a launch carries only its
 // own arithmetic: the flag tests and the dead branches they guard were a fifth of the instructions.
-template <bool INT16, bool DROP, bool HAS_T, bool BOUNDS>
+template <bool INT16, bool DROP, bool HAS_T, bool BOUNDS, bool RAW = false>
 __global__ void __launch_bounds__(UP_THREADS, 3) k_unproject(const __grid_constant__ UnprojParams p)
 {
     __shared__ __align__(128) float2 tab_s[UP_TILE];
@@ -100,7 +103,9 @@ __global__ void __launch_bounds__(UP_THREADS, 3) k_unproject(const __grid_consta
             for (int j = 0; j < UP_PPT; ++j) dz[j] = (px0 + j < npx) ? p.depth[row + j] : (uint16_t)0;
         }
         float out[UP_PPT * 3];
+        float raw[RAW ? UP_PPT * 3 : 1];
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        float rmn[3] = {INFINITY, INFINITY, INFINITY}, rmx[3] = {-INFINITY, -INFINITY, -INFINITY};
         int cnt = 0;
         unsigned okmask = 0;
 #pragma unroll
@@ -131,6 +136,14 @@ __global__ void __launch_bounds__(UP_THREADS, 3) k_unproject(const __grid_consta
                 o[0] = xi; o[1] = yi; o[2] = zi;
             }
             if (DROP && (X == 0.0 || Y == 0.0 || Z == 0.0)) ok = false;
+            if (RAW && s > 0) {
+                const float rx = ok ? (float)X : NAN, ry = ok ? (float)Y : NAN, rz = ok ? (float)Z : NAN;
+                raw[3 * j] = rx; raw[3 * j + 1] = ry; raw[3 * j + 2] = rz;
+                if (ok) {
+                    rmn[0] = fminf(rmn[0], rx); rmn[1] = fminf(rmn[1], ry); rmn[2] = fminf(rmn[2], rz);
+                    rmx[0] = fmaxf(rmx[0], rx); rmx[1] = fmaxf(rmx[1], ry); rmx[2] = fmaxf(rmx[2], rz);
+                }
+            }
             if (HAS_T && ok) {
                 const double x2 = kp_affine(T[0], T[1], T[2], T[3], X, Y, Z);
                 const double y2 = kp_affine(T[4], T[5], T[6], T[7], X, Y, Z);
@@ -139,6 +152,7 @@ __global__ void __launch_bounds__(UP_THREADS, 3) k_unproject(const __grid_consta
             }
             float fx3 = ok ? (float)X : NAN, fy3 = ok ? (float)Y : NAN, fz3 = ok ? (float)Z : NAN;
             out[3 * j] = fx3; out[3 * j + 1] = fy3; out[3 * j + 2] = fz3;
+            if (RAW && s == 0) { raw[3 * j] = fx3; raw[3 * j + 1] = fy3; raw[3 * j + 2] = fz3; }
             if (ok) okmask |= 1u << j;
             if (BOUNDS && ok) {
                 ++cnt;
@@ -155,6 +169,18 @@ __global__ void __launch_bounds__(UP_THREADS, 3) k_unproject(const __grid_consta
 #pragma unroll
             for (int j = 0; j < UP_PPT; ++j)
                 if (px0 + j < npx) { o[3 * j] = out[3 * j]; o[3 * j + 1] = out[3 * j + 1]; o[3 * j + 2] = out[3 * j + 2]; }
+        }
+        if (RAW) {
+            float *r = p.xyz_raw + 3 * row;
+            if (full && vst_ok && ((((uintptr_t)p.xyz_raw) & 15u) == 0u)) {
+                float4 *r4 = reinterpret_cast<float4 *>(r);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) r4[q] = make_float4(raw[4 * q], raw[4 * q + 1], raw[4 * q + 2], raw[4 * q + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < UP_PPT; ++j)
+                    if (px0 + j < npx) { r[3 * j] = raw[3 * j]; r[3 * j + 1] = raw[3 * j + 1]; r[3 * j + 2] = raw[3 * j + 2]; }
+            }
         }
         if (p.valid) {
             if (full && (row % 8 == 0) && ((((uintptr_t)p.valid) & 7u) == 0u)) {
@@ -182,11 +208,31 @@ __global__ void __launch_bounds__(UP_THREADS, 3) k_unproject(const __grid_consta
                 }
                 enc[6] += __shfl_xor_sync(KP_FULL, enc[6], sft);
             }
+            constexpr int NSETS = RAW ? 2 : 1;
             if (lane == 0) {
                 int4 *slot = reinterpret_cast<int4 *>(p.bounds_enc) +
-                             2 * ((((int64_t)b * p.S + s) * gridDim.x + blockIdx.x) * (UP_THREADS / 32) + (tid >> 5));
+                             2 * (((((int64_t)b * p.S + s) * NSETS) * gridDim.x + blockIdx.x) * (UP_THREADS / 32) + (tid >> 5));
                 slot[0] = make_int4(enc[0], enc[1], enc[2], enc[3]);
                 slot[1] = make_int4(enc[4], enc[5], enc[6], 0);
+            }
+            if (RAW) {
+                // set 1: bounds of what went to xyz_raw (the master's are those of set 0)
+                int renc[6] = {kp_f2ord(s ? rmn[0] : mn[0]), kp_f2ord(s ? rmn[1] : mn[1]), kp_f2ord(s ? rmn[2] : mn[2]),
+                               kp_f2ord(s ? rmx[0] : mx[0]), kp_f2ord(s ? rmx[1] : mx[1]), kp_f2ord(s ? rmx[2] : mx[2])};
+#pragma unroll
+                for (int sft = 16; sft >= 1; sft >>= 1) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        renc[c] = min(renc[c], __shfl_xor_sync(KP_FULL, renc[c], sft));
+                        renc[3 + c] = max(renc[3 + c], __shfl_xor_sync(KP_FULL, renc[3 + c], sft));
+                    }
+                }
+                if (lane == 0) {
+                    int4 *slot = reinterpret_cast<int4 *>(p.bounds_enc) +
+                                 2 * (((((int64_t)b * p.S + s) * NSETS + 1) * gridDim.x + blockIdx.x) * (UP_THREADS / 32) + (tid >> 5));
+                    slot[0] = make_int4(renc[0], renc[1], renc[2], renc[3]);
+                    slot[1] = make_int4(renc[4], renc[5], enc[6], 0);
+                }
             }
         }
     }
@@ -335,7 +381,7 @@ int kp_unproject_device(kp_ctx *ctx, const uint16_t *d_depth, const float *d_xyt
                                              (double)S * P * 8.0);
     UnprojParams p;
     p.depth = d_depth; p.tab = (const float2 *)d_xytab; p.B = B; p.S = S; p.P = P; p.flags = flags;
-    p.has_T = h_T != nullptr; p.scale = scale; p.xyz = d_xyz; p.valid = d_valid; p.xyz16 = d_xyz16;
+    p.has_T = h_T != nullptr; p.scale = scale; p.xyz = d_xyz; p.valid = d_valid; p.xyz16 = d_xyz16; p.xyz_raw = nullptr;
     // bounds: the kernel leaves one slot per warp and frame, folded into d_bounds_enc's rows afterwards
     const int64_t ntiles = kp_blocks(P, UP_TILE);
     const int64_t nslots = (int64_t)B * S * ntiles * (UP_THREADS / 32);
@@ -360,6 +406,44 @@ int kp_unproject_device(kp_ctx *ctx, const uint16_t *d_depth, const float *d_xyt
         KP_LAUNCH_CHECK(ctx);
     }
     return KP_OK;
+}
+
+// frame engine: B frames in one launch; fused cloud [B][S*P][3] in the master frame + ICP inputs [B][S][P][3]
+// (s = 0: the transformed master, s >= 1: the sub cloud in its own frame) + bounds rows [B][S][2][8] (set 0: fused
+// coordinates of sensor s, set 1: what went to the ICP input).  d_slots: [B*S*2*tiles*8 warps][8] int32 scratch.
+int kp_unproject_engine(kp_ctx *ctx, const uint16_t *d_depth, const float *d_xytab, const double *h_T, int B, int S, int64_t P,
+                        int flags, double scale, float *d_xyz, float *d_xyz_raw, int32_t *d_slots, int32_t *d_rows)
+{
+    if (B <= 0 || S <= 0 || P <= 0) return KP_OK;
+    if (S > UP_MAX_S) return kp_set_err(ctx, KP_E_ARG, "frame engine: at most %d sensors (got %d)", UP_MAX_S, S);
+    KP_PROFB(ctx, "unproject_transform", (double)B * S * P * (2.0 + 12.0 + 12.0) + (double)S * P * 8.0);
+    UnprojParams p;
+    p.depth = d_depth; p.tab = (const float2 *)d_xytab; p.B = B; p.S = S; p.P = P; p.flags = flags;
+    p.has_T = 1; p.scale = scale; p.xyz = d_xyz; p.valid = nullptr; p.xyz16 = nullptr; p.xyz_raw = d_xyz_raw;
+    p.bounds_enc = d_slots;
+    for (int s = 0; s < UP_MAX_S; ++s) fill_T12(h_T && s < S ? h_T + 16 * s : nullptr, p.T[s]);
+    const int64_t ntiles = kp_blocks(P, UP_TILE);
+    dim3 grid((unsigned)ntiles, (unsigned)S);
+    const int variant = ((flags & KP_UNPROJECT_INT16) ? 1 : 0) | ((flags & KP_UNPROJECT_DROP_ANY_ZERO) ? 2 : 0) | (d_xyz_raw ? 4 : 0);
+    switch (variant) {
+    case 0: k_unproject<false, false, true, true, false><<<grid, UP_THREADS, 0, ctx->stream>>>(p); break;
+    case 1: k_unproject<true, false, true, true, false><<<grid, UP_THREADS, 0, ctx->stream>>>(p); break;
+    case 2: k_unproject<false, true, true, true, false><<<grid, UP_THREADS, 0, ctx->stream>>>(p); break;
+    case 3: k_unproject<true, true, true, true, false><<<grid, UP_THREADS, 0, ctx->stream>>>(p); break;
+    case 4: k_unproject<false, false, true, true, true><<<grid, UP_THREADS, 0, ctx->stream>>>(p); break;
+    case 5: k_unproject<true, false, true, true, true><<<grid, UP_THREADS, 0, ctx->stream>>>(p); break;
+    case 6: k_unproject<false, true, true, true, true><<<grid, UP_THREADS, 0, ctx->stream>>>(p); break;
+    default: k_unproject<true, true, true, true, true><<<grid, UP_THREADS, 0, ctx->stream>>>(p); break;
+    }
+    KP_LAUNCH_CHECK(ctx);
+    // rows [B][S][sets][8]: one set without the ICP inputs, two with
+    k_bounds_fold<<<B * S * (d_xyz_raw ? 2 : 1), 256, 0, ctx->stream>>>(d_slots, ntiles * (UP_THREADS / 32), d_rows);
+    KP_LAUNCH_CHECK(ctx);
+    return KP_OK;
+}
+size_t kp_unproject_engine_slots(int B, int S, int64_t P)
+{
+    return (size_t)B * S * 2 * kp_blocks(P, UP_TILE) * (UP_THREADS / 32) * 8;
 }
 
 extern "C" {

@@ -1,6 +1,8 @@
 """Batched whole-frame driver (BASELINE config C4) over ``kp_pipeline_*`` of the C ABI.
 
-One ``FramePipeline`` = one GPU.  It replaces, for a stream of synchronised multi-sensor depth
+One ``FramePipeline`` = one GPU, driven by one host thread: frames go through the device in batches of B frames
+per kernel launch with every intermediate count kept on the device (a CUDA graph per batch slot), so a call makes
+no host round trip until its last batch is enqueued.  It replaces, for a stream of synchronised multi-sensor depth
 frames, the per-frame body of ``DataProcessor.__init__`` (``preprocessing/data.py:35-69``: transform,
 fuse, ``filter_outliers``) followed by the ``floor_removal.py:64-73`` loop body and a per-frame
 ``execute_point_to_plane_registration`` refinement of every sub sensor's extrinsic
@@ -162,6 +164,12 @@ class FramePipeline:
         if rc != 0:
             self._raise(rc)
         return res
+
+    def frames_in_flight(self):
+        """(frames per kernel launch, batch slots in flight) the pipeline was built with."""
+        b, w = C.c_int(), C.c_int()
+        self.lib.kp_pipeline_frames_in_flight(self.handle, C.byref(b), C.byref(w))
+        return b.value, w.value
 
     def launch_count(self) -> int:
         return int(self.lib.kp_pipeline_launch_count(self.handle))
