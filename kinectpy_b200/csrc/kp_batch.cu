@@ -65,6 +65,7 @@ struct FRunHead {
 };
 struct ERows {
     const float *in; float *out; int64_t stride;     // stride in rows
+    const uint32_t *aux_in; uint32_t *aux_out;
     __device__ void operator()(int seg, int64_t i, bool f, int pos) const
     {
         if (!f) return;
@@ -72,17 +73,21 @@ struct ERows {
         float *o = out + 3 * (seg * stride + pos);
         const float x = a[0], y = a[1], z = a[2];
         o[0] = x; o[1] = y; o[2] = z;
+        if (aux_in) aux_out[seg * stride + pos] = aux_in[seg * stride + i];
     }
 };
 struct EPart {
     const float *in; float *out_t; float *out_f; int64_t stride;
+    const uint32_t *aux_in; uint32_t *aux_t; uint32_t *aux_f;
     __device__ void operator()(int seg, int64_t i, bool f, int pos) const
     {
         // pos = number of set flags before i: a cleared row lands at i - pos among the cleared ones
         const float *a = in + 3 * (seg * stride + i);
-        float *o = (f ? out_t + 3 * (seg * stride + pos) : out_f + 3 * (seg * stride + (i - pos)));
+        const int64_t dst = seg * stride + (f ? (int64_t)pos : i - pos);
+        float *o = (f ? out_t : out_f) + 3 * dst;
         const float x = a[0], y = a[1], z = a[2];
         o[0] = x; o[1] = y; o[2] = z;
+        if (aux_in) (f ? aux_t : aux_f)[dst] = aux_in[seg * stride + i];
     }
 };
 struct EIndex {
@@ -339,16 +344,17 @@ __global__ void __launch_bounds__(1024) k_bcsum_rest(DCnt n, double *tmp, int64_
 }  // namespace
 
 int kp_b_compact_rows(const BLaunch &L, const BScan &S, DCnt n, const uint8_t *mask, int64_t mask_stride, int invert,
-                      const float *in, float *out, int64_t row_stride, DOut total)
+                      const float *in, float *out, int64_t row_stride, DOut total, const uint32_t *aux_in, uint32_t *aux_out)
 {
     KP_PROFB(L.ctx, "compact_rows", 0.0);
-    return bc_run(L, S, n, FMask{mask, mask_stride, invert}, ERows{in, out, row_stride}, total);
+    return bc_run(L, S, n, FMask{mask, mask_stride, invert}, ERows{in, out, row_stride, aux_in, aux_out}, total);
 }
 int kp_b_partition_rows(const BLaunch &L, const BScan &S, DCnt n, const uint8_t *mask, int64_t mask_stride, const float *in,
-                        float *out_true, float *out_false, int64_t row_stride, DOut total)
+                        float *out_true, float *out_false, int64_t row_stride, DOut total, const uint32_t *aux_in,
+                        uint32_t *aux_true, uint32_t *aux_false)
 {
     KP_PROFB(L.ctx, "compact_rows", 0.0);
-    return bc_run(L, S, n, FMask{mask, mask_stride, 0}, EPart{in, out_true, out_false, row_stride}, total);
+    return bc_run(L, S, n, FMask{mask, mask_stride, 0}, EPart{in, out_true, out_false, row_stride, aux_in, aux_true, aux_false}, total);
 }
 int kp_b_compact_index(const BLaunch &L, const BScan &S, DCnt n, const uint8_t *mask, int64_t mask_stride, int32_t *list,
                        int64_t list_stride, DOut total)

@@ -9,6 +9,7 @@
 #pragma once
 #include "kp_common.cuh"
 #include "kp_grid.cuh"
+#include "kp_vbi.cuh"
 
 // count of segment s = p[s * stride]  (stride in int32 units: counts usually sit in a per-frame state struct)
 struct DCnt {
@@ -34,6 +35,7 @@ struct KpVoxDev {
     double voxel;
     int sh_x, sh_y;
     unsigned int sentinel;     // key of absent (NaN) rows: one bit above the packed index
+    int imax[3];               // largest voxel index per axis
     int ok;                    // 0: the cloud is empty or its extent does not fit 31 key bits
 };
 
@@ -58,11 +60,14 @@ struct BScan {
 
 // ---- compaction family (count + last-CTA scan, then scatter): no CTA ever waits for another one
 // rows of `in` whose mask byte (xor invert) is set -> packed into `out`; total[seg] = rows kept
+// aux_in / aux_out (nullable): a 4-byte payload per row (its packed voxel coordinates) that travels with the row
 int kp_b_compact_rows(const BLaunch &L, const BScan &S, DCnt n, const uint8_t *mask, int64_t mask_stride, int invert,
-                      const float *in, float *out, int64_t row_stride, DOut total);
+                      const float *in, float *out, int64_t row_stride, DOut total, const uint32_t *aux_in = nullptr,
+                      uint32_t *aux_out = nullptr);
 // rows with mask set -> out_true (packed), the others -> out_false (packed, order kept); total[seg] = rows in out_true
 int kp_b_partition_rows(const BLaunch &L, const BScan &S, DCnt n, const uint8_t *mask, int64_t mask_stride, const float *in,
-                        float *out_true, float *out_false, int64_t row_stride, DOut total);
+                        float *out_true, float *out_false, int64_t row_stride, DOut total, const uint32_t *aux_in = nullptr,
+                        uint32_t *aux_true = nullptr, uint32_t *aux_false = nullptr);
 // positions of set mask bytes -> list[seg][..] (ascending); total[seg] = list length
 int kp_b_compact_index(const BLaunch &L, const BScan &S, DCnt n, const uint8_t *mask, int64_t mask_stride, int32_t *list,
                        int64_t list_stride, DOut total);
@@ -92,6 +97,7 @@ int kp_b_csum(const BLaunch &L, DCnt n, const double *x, int64_t x_stride, int m
 // coarse grid build in between
 struct KpKnnSegDesc {
     const KpGridDev *g0, *g1;     // device: level-0 / level-1 grid of this cloud
+    const KpVbiDev *vbi;          // device, nullable: voxel-brick index of this cloud (level 0 runs on it when it was built)
     const float4 *pts0;           // the level-0 grid's cell-sorted rows (static pointer)
     const int32_t *n;             // device: points in the cloud (every point is a query)
     uint8_t *flags0, *flags1;     // [cap] "not certified at level 0 / 1", indexed by level-0 position
@@ -102,11 +108,14 @@ struct KpKnnSegDesc {
     float *normals;               // normals mode: output
 };
 struct KpKnnBatch {
-    void *d_params = nullptr;
-    int nseg = 0, k = 0, mode = 0, cap_hist = 0, cap_warp = 0;
+    void *d_params = nullptr, *h_params = nullptr;     // [3 levels][nseg] parameter blocks on the device and their host copy
+    int nseg = 0, k = 0, mode = 0, cap_hist = 0, cap_warp = 0, rad = 1;
 };
 // mode 0: mean distance of the k nearest (SOR); mode 1: normals from the <= k nearest inside `radius`
-int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, int mode, double radius, KpKnnBatch *out);
+// rho_a / rho_b: the two search radii of the voxel-brick level 0 (ignored without an index)
+int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, int mode, double radius, double rho_a, double rho_b,
+                        KpKnnBatch *out);
+int kp_knn_batch_vbi(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows);
 void kp_knn_batch_destroy(KpKnnBatch *b);
 int kp_knn_batch_level0(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows);
 int kp_knn_batch_level1(kp_ctx *ctx, const KpKnnBatch &b);
@@ -116,6 +125,7 @@ int kp_knn_batch_stragglers(kp_ctx *ctx, const KpKnnBatch &b);
 // (blockIdx.y = pair); max_iter + 1 identical pass launches, a converged pair's CTAs return at once
 struct KpIcpPairDesc {
     const KpGridDev *tgt_grid;    // device: grid over the target (cell >= max_corr)
+    const KpVbiDev *tgt_vbi;      // device, nullable: voxel-brick index over the target (preferred when it was built)
     const float *tgt_normals;     // by original target index
     const float *src;             // source cloud (device), n_src rows
     const int32_t *n_src;         // device

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include "../../include/kp_api.h"
@@ -161,7 +162,11 @@ int kp_grid_auto_cell(kp_ctx *ctx, const float *d_xyz, int64_t n, const float *h
 // cell edge for a k-nearest search on a cloud that was voxel-downsampled at `voxel`
 // (1.5 x the k-neighbour radius of an ideal 1-point-per-voxel surface: sensor clouds are sparser than the
 // voxel grid far from the camera; sweep in profiles/r01_c_knn_base_coarse_sweep.log)
-static inline double kp_knn_cell_from_voxel(double voxel, int k) { return voxel * 1.5 * sqrt((double)k / 3.14159265358979); }
+static inline double kp_knn_cell_from_voxel(double voxel, int k)
+{
+    static const double mult = getenv("KP_KNN_CELL_MULT") ? atof(getenv("KP_KNN_CELL_MULT")) : 1.5;
+    return voxel * mult * sqrt((double)k / 3.14159265358979);
+}
 
 // internal forms used by the public API and by the frame pipeline (device pointers, async)
 int kp_knn_device(kp_ctx *ctx, const KpGrid &g, const float *d_queries, int64_t nq, int k, double radius,

@@ -37,10 +37,12 @@ struct EngDyn {
     int32_t status, floor_skip, ymax_enc, pad0;
     int32_t nocc[4];                    // occupied cells of grid g[0..3]
     int32_t cnt_l0[3], cnt_l1[3];       // level-0 / level-1 leftover lists of the three neighbour searches
+    int32_t n_old[3], pad2;             // points the GRID level 0 has to search: 0 when the voxel-brick index was built
     int32_t ransac_best, ransac_ncand, ransac_cand[ENG_MAX_CAND];
     float b6[6];                        // bounds of the fused cloud
     KpVoxDev vox_fused;
     KpGridDev g[4];                     // [0],[1]: level 0 / 1 of the main branch, [2],[3]: of the ICP target
+    KpVbiDev vbi[2];                    // voxel-brick index: [0] main branch (SOR clouds), [1] ICP target
     double sor_sum, sor_sq, sor_stats[3];
     double plane[4];
     double cand_sq[ENG_MAX_CAND];
@@ -59,7 +61,7 @@ __device__ __forceinline__ int bit_length_dev(long long v)
 __device__ void vox_setup(const float *b6, int nvalid, double voxel, KpVoxDev &vp, int32_t &status)
 {
     vp.voxel = voxel; vp.ok = 0; vp.sh_x = vp.sh_y = 0; vp.sentinel = 0xffffffffu;
-    for (int c = 0; c < 3; ++c) vp.minb[c] = 0.0;
+    for (int c = 0; c < 3; ++c) { vp.minb[c] = 0.0; vp.imax[c] = 0; }
     if (nvalid <= 0) return;
     int bits[3];
     for (int c = 0; c < 3; ++c) {
@@ -68,6 +70,7 @@ __device__ void vox_setup(const float *b6, int nvalid, double voxel, KpVoxDev &v
         if (__dmul_rn(voxel, 2147483647.0) < __dsub_rn(maxb, vp.minb[c])) { status = KP_E_RANGE; return; }
         const long long imax = (long long)floor(__ddiv_rn(__dsub_rn((double)b6[3 + c], vp.minb[c]), voxel));
         bits[c] = bit_length_dev(imax);
+        vp.imax[c] = (int)(imax < 0x7fffffff ? imax : 0x7fffffff);
     }
     vp.sh_y = bits[2];
     vp.sh_x = bits[2] + bits[1];
@@ -156,6 +159,9 @@ struct VoxMeanArgs {
     const int32_t *run_start; int64_t rs_stride;
     DCnt R;
     float *out; int64_t out_stride;
+    const uint32_t *keys; int64_t key_stride;          // sorted keys (voxel index of a run = key of its first row)
+    const KpVoxDev *vp; int64_t vp_stride;
+    uint32_t *vijk;                                    // nullable: packed voxel coordinates per output row (stride out_stride)
 };
 __global__ void __launch_bounds__(128) k_e_voxel_mean(const __grid_constant__ VoxMeanArgs a)
 {
@@ -177,6 +183,12 @@ __global__ void __launch_bounds__(128) k_e_voxel_mean(const __grid_constant__ Vo
         out[3 * (int64_t)r] = (float)__ddiv_rn(sx, cnt);
         out[3 * (int64_t)r + 1] = (float)__ddiv_rn(sy, cnt);
         out[3 * (int64_t)r + 2] = (float)__ddiv_rn(sz, cnt);
+        if (a.vijk) {
+            const KpVoxDev &vp = vox_of(a.vp, a.vp_stride, seg);
+            const uint32_t key = a.keys[seg * a.key_stride + lo];
+            const uint32_t ix = key >> vp.sh_x, iy = (key >> vp.sh_y) & ((1u << (vp.sh_x - vp.sh_y)) - 1u), iz = key & ((1u << vp.sh_y) - 1u);
+            a.vijk[seg * a.out_stride + r] = (ix << 20) | ((iy & 1023u) << 10) | (iz & 1023u);   // (10 bits each: checked by the index build)
+        }
     }
 }
 
@@ -402,6 +414,179 @@ __global__ void __launch_bounds__(256) k_eg_scatter(const __grid_constant__ Grid
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int pos = rs[rank[i]] + loc[i];
         sorted[pos] = make_float4(xyz[3 * (int64_t)i], xyz[3 * (int64_t)i + 1], xyz[3 * (int64_t)i + 2], __int_as_float(i));
+    }
+}
+
+// ---------------------------------------------------------------- voxel-brick index (kp_vbi.cuh)
+struct VbiArgs {
+    KpVbiDev *v; int64_t v_stride;                  // bytes between the segments' index structs
+    const float *xyz; int64_t xyz_stride;           // rows
+    const uint32_t *vijk; int64_t vijk_stride;
+    DCnt n;
+    const KpVoxDev *vp; int64_t vp_stride;
+    uint2 *bricks; int64_t brick_stride; int64_t cap_bricks;
+    float4 *pts; uint32_t *vijk_sorted; int64_t pts_stride;
+    int32_t *status; int64_t status_stride;         // int units
+};
+__device__ __forceinline__ KpVbiDev &vbi_of(KpVbiDev *v, int64_t stride_bytes, int seg)
+{
+    return *reinterpret_cast<KpVbiDev *>(reinterpret_cast<char *>(v) + seg * stride_bytes);
+}
+__global__ void k_vbi_setup(const __grid_constant__ VbiArgs a)
+{
+    const int seg = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    KpVbiDev &v = vbi_of(a.v, a.v_stride, seg);
+    const KpVoxDev &vp = vox_of(a.vp, a.vp_stride, seg);
+    const int n = a.n.at(seg);
+    v.bricks = a.bricks + seg * a.brick_stride;
+    v.pts = a.pts + seg * a.pts_stride;
+    v.vijk = a.vijk_sorted + seg * a.pts_stride;
+    v.voxel = vp.voxel; v.inv_voxel = 1.0 / vp.voxel;
+    v.npts = 0; v.ok = 0; v.eps = 0.0;
+    double nbricks = 1.0, M = 0.0;
+    bool fits = vp.ok && n > 0;
+    for (int c = 0; c < 3; ++c) {
+        v.minb[c] = vp.minb[c];
+        const int sh = c == 0 ? 1 : 2;                // bricks of 2 x 4 x 4 voxels
+        v.nb[c] = (vp.imax[c] >> sh) + 1 + 2 * KP_VBI_PAD;
+        v.nvox[c] = ((vp.imax[c] >> sh) + 1) << sh;
+        if (vp.imax[c] >= 1024) fits = false;
+        nbricks *= (double)v.nb[c];
+        M = fmax(M, fmax(fabs(vp.minb[c]), fabs(vp.minb[c] + vp.voxel * (double)v.nvox[c])));
+    }
+    if (nbricks > (double)a.cap_bricks) fits = false;
+    if (!fits) { v.nb[0] = v.nb[1] = v.nb[2] = 0; return; }
+    v.eps = M * (1.0 / 4194304.0);                  // 4 ulp of the largest float32 coordinate
+    v.npts = n;
+    v.ok = 1;
+}
+__global__ void __launch_bounds__(256) k_vbi_clear(const __grid_constant__ VbiArgs a)
+{
+    const int seg = blockIdx.y;
+    const KpVbiDev &v = vbi_of(a.v, a.v_stride, seg);
+    if (!v.ok) return;
+    const long long nb = (long long)v.nb[0] * v.nb[1] * v.nb[2];
+    uint2 *br = a.bricks + seg * a.brick_stride;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += (long long)gridDim.x * blockDim.x) br[i] = make_uint2(0u, 0u);
+}
+__device__ __forceinline__ void vbi_locate(const KpVbiDev &v, uint32_t ijk, long long &L, unsigned &bit)
+{
+    const int ix = (int)(ijk >> 20), iy = (int)((ijk >> 10) & 1023u), iz = (int)(ijk & 1023u);
+    L = kp_vbi_brick_index(v, ix >> 1, iy >> 2, iz >> 2);
+    bit = (unsigned)((ix & 1) * 16 + (iy & 3) * 4 + (iz & 3));
+}
+__global__ void __launch_bounds__(256) k_vbi_mark(const __grid_constant__ VbiArgs a)
+{
+    const int seg = blockIdx.y;
+    const KpVbiDev v = vbi_of(a.v, a.v_stride, seg);
+    if (!v.ok) return;
+    const uint32_t *vijk = a.vijk + seg * a.vijk_stride;
+    uint2 *br = a.bricks + seg * a.brick_stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.npts; i += gridDim.x * blockDim.x) {
+        long long L; unsigned bit;
+        vbi_locate(v, vijk[i], L, bit);
+        const unsigned m = 1u << bit;
+        // a second point in the same voxel cannot happen on a voxel-downsampled cloud; if it does, say so
+        if (atomicOr(&br[L].x, m) & m) a.status[seg * a.status_stride] = KP_E_RANGE;
+    }
+}
+__global__ void __launch_bounds__(256) k_vbi_rank_reduce(const __grid_constant__ VbiArgs a, BScan S)
+{
+    __shared__ int wc[8];
+    __shared__ int carry_s;
+    __shared__ int wtot[8];
+    const int seg = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const KpVbiDev &v = vbi_of(a.v, a.v_stride, seg);
+    const long long nb = v.ok ? (long long)v.nb[0] * v.nb[1] * v.nb[2] : 0;
+    const int ntiles = (int)((nb + BC_TILE - 1) / BC_TILE);
+    const uint2 *br = a.bricks + seg * a.brick_stride;
+    int32_t *ts = S.tile_sum + (size_t)seg * S.max_tiles;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int s = 0;
+#pragma unroll
+        for (int j = 0; j < BC_ITEMS; ++j) {
+            const long long i = (long long)tile * BC_TILE + j * BC_THREADS + threadIdx.x;
+            if (i < nb) s += __popc(br[i].x);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(KP_FULL, s, d);
+        if (lane == 0) wc[w] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int ww = 0; ww < 8; ++ww) t += wc[ww]; ts[tile] = t; }
+        __syncthreads();
+    }
+    if (!eg_last_block(S.ticket + seg)) return;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += BC_THREADS) {
+        const int i = base + threadIdx.x;
+        const int x = i < ntiles ? __ldcg(ts + i) : 0;
+        int incl = x;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { const int y = __shfl_up_sync(KP_FULL, incl, s); if (lane >= s) incl += y; }
+        if (lane == 31) wtot[w] = incl;
+        __syncthreads();
+        int woff = 0;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) woff += ww < w ? wtot[ww] : 0;
+        const int excl = carry_s + woff + incl - x;
+        if (i < ntiles) ts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == BC_THREADS - 1) carry_s = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) S.ticket[seg] = 0;
+}
+__global__ void __launch_bounds__(256) k_vbi_rank_apply(const __grid_constant__ VbiArgs a, BScan S)
+{
+    __shared__ int wtot[8];
+    const int seg = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const KpVbiDev &v = vbi_of(a.v, a.v_stride, seg);
+    const long long nb = v.ok ? (long long)v.nb[0] * v.nb[1] * v.nb[2] : 0;
+    const int ntiles = (int)((nb + BC_TILE - 1) / BC_TILE);
+    uint2 *br = a.bricks + seg * a.brick_stride;
+    const int32_t *ts = S.tile_sum + (size_t)seg * S.max_tiles;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long i0 = (long long)tile * BC_TILE + (long long)threadIdx.x * BC_ITEMS;
+        int c[BC_ITEMS];
+        int s = 0;
+#pragma unroll
+        for (int j = 0; j < BC_ITEMS; ++j) {
+            c[j] = i0 + j < nb ? __popc(br[i0 + j].x) : 0;
+            s += c[j];
+        }
+        int incl = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(KP_FULL, incl, d); if (lane >= d) incl += y; }
+        if (lane == 31) wtot[w] = incl;
+        __syncthreads();
+        int run = ts[tile] + incl - s;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) run += ww < w ? wtot[ww] : 0;
+#pragma unroll
+        for (int j = 0; j < BC_ITEMS; ++j) { if (c[j]) br[i0 + j].y = (unsigned)run; run += c[j]; }   // only occupied bricks are ever asked
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_vbi_scatter(const __grid_constant__ VbiArgs a)
+{
+    const int seg = blockIdx.y;
+    const KpVbiDev v = vbi_of(a.v, a.v_stride, seg);
+    if (!v.ok) return;
+    const float *xyz = a.xyz + 3 * seg * a.xyz_stride;
+    const uint32_t *vijk = a.vijk + seg * a.vijk_stride;
+    const uint2 *br = a.bricks + seg * a.brick_stride;
+    float4 *pts = a.pts + seg * a.pts_stride;
+    uint32_t *vs = a.vijk_sorted + seg * a.pts_stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.npts; i += gridDim.x * blockDim.x) {
+        long long L; unsigned bit;
+        const uint32_t ijk = vijk[i];
+        vbi_locate(v, ijk, L, bit);
+        const uint2 e = br[L];
+        const int pos = (int)e.y + __popc(e.x & ((1u << bit) - 1u));
+        pts[pos] = make_float4(xyz[3 * (int64_t)i], xyz[3 * (int64_t)i + 1], xyz[3 * (int64_t)i + 2], __int_as_float(i));
+        vs[pos] = ijk;
     }
 }
 
@@ -699,7 +884,7 @@ __global__ void __launch_bounds__(256) k_e_plane_mask(const __grid_constant__ Ra
 }
 
 // rows src[0..n) appended to dst at row offset off[seg]; total[seg] = off + n
-struct AppendArgs { const float *src; float *dst; int64_t stride; DCnt n, off; DOut total; };
+struct AppendArgs { const float *src; float *dst; int64_t stride; DCnt n, off; DOut total; const uint32_t *aux_src; uint32_t *aux_dst; };
 __global__ void __launch_bounds__(256) k_e_append_rows(const __grid_constant__ AppendArgs a)
 {
     const int seg = blockIdx.y;
@@ -707,6 +892,9 @@ __global__ void __launch_bounds__(256) k_e_append_rows(const __grid_constant__ A
     const float *src = a.src + 3 * seg * a.stride;
     float *dst = a.dst + 3 * (seg * a.stride + off);
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < 3LL * n; e += (int64_t)gridDim.x * blockDim.x) dst[e] = src[e];
+    if (a.aux_src)
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+            a.aux_dst[seg * a.stride + off + e] = a.aux_src[seg * a.stride + e];
     if (blockIdx.x == 0 && threadIdx.x == 0) a.total.at(seg) = off + n;
 }
 // n_up = n_sor - n_lo is not stored anywhere: a tiny kernel derives the per-frame scalars between stages
@@ -715,6 +903,16 @@ __global__ void k_e_derive_up(const __grid_constant__ DeriveArgs a, int B)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f < B) a.n_up[f] = a.dyn[f].n_sor - a.dyn[f].n_lo;
+}
+
+// points left to the grid level 0: none when the cloud's voxel-brick index was built
+struct NoldArgs { const KpVbiDev *vbi; int64_t vbi_stride; DCnt n; DOut n_old; };
+__global__ void k_e_nold(const __grid_constant__ NoldArgs a, int nseg)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    const KpVbiDev &v = *reinterpret_cast<const KpVbiDev *>(reinterpret_cast<const char *>(a.vbi) + s * a.vbi_stride);
+    a.n_old.at(s) = v.ok ? 0 : a.n.at(s);
 }
 
 // final cloud + result record of every frame
@@ -812,6 +1010,8 @@ struct EngSlot {
     uint8_t *flags[2] = {nullptr, nullptr}, *mask = nullptr, *mask2 = nullptr;
     int32_t *list[2] = {nullptr, nullptr};
     int32_t *n_up = nullptr, *sink = nullptr, *isink = nullptr;
+    uint32_t *vA = nullptr, *vB = nullptr, *vC = nullptr, *vD = nullptr, *vE = nullptr, *vsorted = nullptr;   // packed voxel coordinates of A, Bb, C, D, E
+    uint2 *bricks = nullptr;
     double4 *planes = nullptr; uint8_t *pvalid = nullptr; unsigned long long *hcnt = nullptr; double *tie_slots = nullptr;
     KpKnnBatch knn_sor, knn_fsor, knn_nrm;
     // ICP branch
@@ -827,6 +1027,8 @@ struct EngSlot {
     uint8_t *iflags[2] = {nullptr, nullptr};
     int32_t *ilist[2] = {nullptr, nullptr};
     float *nrm = nullptr;                             // [B][P][3]
+    uint32_t *ivijk = nullptr, *ivijk_sorted = nullptr;   // packed voxel coordinates of the ICP clouds / of the indexed target
+    uint2 *ibricks = nullptr;
     KpIcpBatch icp;
 };
 }  // namespace
@@ -836,8 +1038,11 @@ struct kp_pipeline {
     int device = 0;
     int B = 1, W = 1;                 // frames per batch, batch slots in flight
     int64_t cap_cells = 1 << 25;
+    int64_t cap_bricks = 1 << 23;
     int64_t NPr = 0, Pr = 0;          // row strides of the engine's own arrays: S*P and P rounded up to 64 (aligned vector access)
-    bool use_graph = true, profiling = false;
+    bool use_graph = true, profiling = false, use_vbi_icp = false, use_vbi_knn = false;
+    double rho_mult_a = 1.15, rho_mult_b = 2.0;
+    int knn_rad = 1;                  // level-0 block radius in cells (KP_KNN_RAD): 1 = 27 cells of the full edge, 2 = 125 cells of half the edge
     std::vector<EngSlot> slots;
     float *d_tab = nullptr;
     std::vector<double> T_fuse, T_icp;
@@ -878,7 +1083,8 @@ inline int ctas_for(const kp_pipeline *pl, int per_sm) { return pl->sm_count * p
 // ---- stage: voxel downsample of `nseg` clouds of `n` rows each
 int stage_voxel(kp_pipeline *pl, kp_ctx *ctx, int nseg, int64_t n, const float *xyz, int64_t xyz_stride, const KpVoxDev *vp,
                 int64_t vp_stride, DCnt nvalid, uint32_t *keys, uint32_t *keys_tmp, int32_t *vals, int32_t *vals_tmp, int64_t kstride,
-                const BSort &sw, const BScan &sc, int32_t *run_start, int64_t rs_stride, float *out, int64_t out_stride, DOut m)
+                const BSort &sw, const BScan &sc, int32_t *run_start, int64_t rs_stride, float *out, int64_t out_stride, DOut m,
+                uint32_t *vijk = nullptr)
 {
     {
         KP_PROFB(ctx, "voxel_keys", (double)nseg * n * 16.0);
@@ -893,7 +1099,7 @@ int stage_voxel(kp_pipeline *pl, kp_ctx *ctx, int nseg, int64_t n, const float *
     KP_TRY(kp_b_run_starts_u32(L, sc, nvalid, keys, kstride, run_start, rs_stride, m));
     {
         KP_PROFB(ctx, "voxel_mean", (double)nseg * n * 16.0);
-        VoxMeanArgs a{xyz, xyz_stride, vals, kstride, run_start, rs_stride, DCnt{m.p, m.stride}, out, out_stride};
+        VoxMeanArgs a{xyz, xyz_stride, vals, kstride, run_start, rs_stride, DCnt{m.p, m.stride}, out, out_stride, keys, kstride, vp, vp_stride, vijk};
         int64_t gx = (n + 127) / 128;
         if (gx > ctas_for(pl, 16)) gx = ctas_for(pl, 16);
         k_e_voxel_mean<<<dim3((unsigned)gx, (unsigned)nseg), 128, 0, ctx->stream>>>(a);
@@ -931,19 +1137,55 @@ int stage_grid(kp_pipeline *pl, kp_ctx *ctx, const GridArgs &a, int nseg, int64_
     return KP_OK;
 }
 
-// ---- stage: exact k nearest of every point of `nseg` clouds (level 0 -> level 1 on a coarser grid -> stragglers)
+// ---- stage: voxel-brick index of `nseg` voxel-downsampled clouds
+int stage_vbi(kp_pipeline *pl, kp_ctx *ctx, const VbiArgs &a, int nseg, const BScan &sc)
+{
+    KP_PROFB(ctx, "vbi_build", 0.0);
+    const int ctas = ctas_for(pl, 4);
+    const dim3 grid((unsigned)ctas, (unsigned)nseg);
+    k_vbi_setup<<<nseg, 32, 0, ctx->stream>>>(a);
+    KP_LAUNCH_CHECK(ctx);
+    k_vbi_clear<<<grid, 256, 0, ctx->stream>>>(a);
+    KP_LAUNCH_CHECK(ctx);
+    k_vbi_mark<<<grid, 256, 0, ctx->stream>>>(a);
+    KP_LAUNCH_CHECK(ctx);
+    const int64_t tiles = (a.cap_bricks + BC_TILE - 1) / BC_TILE;
+    const dim3 bgrid((unsigned)(tiles < ctas ? tiles : ctas), (unsigned)nseg);
+    k_vbi_rank_reduce<<<bgrid, 256, 0, ctx->stream>>>(a, sc);
+    KP_LAUNCH_CHECK(ctx);
+    k_vbi_rank_apply<<<bgrid, 256, 0, ctx->stream>>>(a, sc);
+    KP_LAUNCH_CHECK(ctx);
+    k_vbi_scatter<<<grid, 256, 0, ctx->stream>>>(a);
+    KP_LAUNCH_CHECK(ctx);
+    return KP_OK;
+}
+
+// ---- stage: exact k nearest of every point of `nseg` clouds
+// level 0 on the voxel-brick index (on the grid for a cloud whose index could not be built) -> level 1 on a coarser
+// grid -> ring-expanding stragglers
 struct KnnStage {
     const KpKnnBatch *batch;
-    GridArgs coarse;                 // level-1 grid build (parent = the level-0 grid)
+    bool vbi;                        // the clouds have a voxel-brick index (vbi_args): level 0 runs on it
+    VbiArgs vbi_args;
+    DOut n_old;                      // points left to the grid level 0 (all of them without an index)
+    GridArgs fine, coarse;           // level-0 grid (fallback) and level-1 grid
     uint8_t *flags0, *flags1; int64_t flag_stride;
     int32_t *list0, *list1; int64_t list_stride;
     DOut cnt0, cnt1;
     DCnt n;
 };
-int stage_knn(kp_pipeline *pl, kp_ctx *ctx, const KnnStage &k, int nseg, int64_t cap_rows, const BScan &sc, DOut sink)
+int stage_knn(kp_pipeline *pl, kp_ctx *ctx, const KnnStage &k, int nseg, int64_t cap_rows, const BScan &sc, DOut sink, bool build_vbi)
 {
     BLaunch L{ctx, nseg, cap_rows, ctas_for(pl, 4)};
+    if (k.vbi) {
+        if (build_vbi) KP_TRY(stage_vbi(pl, ctx, k.vbi_args, nseg, sc));
+        NoldArgs na{k.vbi_args.v, k.vbi_args.v_stride, k.n, k.n_old};
+        k_e_nold<<<kp_blocks(nseg, 64), 64, 0, ctx->stream>>>(na, nseg);
+        KP_LAUNCH_CHECK(ctx);
+    }
+    KP_TRY(stage_grid(pl, ctx, k.fine, nseg, cap_rows, sc, sink));          // (over n_old points: nothing when the index exists)
     KP_CUDA(ctx, cudaMemsetAsync(k.flags0, 0, (size_t)nseg * k.flag_stride, ctx->stream));
+    if (k.vbi) KP_TRY(kp_knn_batch_vbi(ctx, *k.batch, cap_rows));
     KP_TRY(kp_knn_batch_level0(ctx, *k.batch, cap_rows));
     KP_TRY(kp_b_compact_index(L, sc, k.n, k.flags0, k.flag_stride, k.list0, k.list_stride, k.cnt0));
     KP_TRY(stage_grid(pl, ctx, k.coarse, nseg, cap_rows, sc, sink));
@@ -957,6 +1199,7 @@ int stage_knn(kp_pipeline *pl, kp_ctx *ctx, const KnnStage &k, int nseg, int64_t
 #define DYN_CNT(slot, field) dcnt(&(slot).dyn->field, sizeof(EngDyn))
 #define DYN_OUT(slot, field) dout(&(slot).dyn->field, sizeof(EngDyn))
 
+// level 0: cell for the k-neighbour radius, over the points the index did not take; level 1: three times that cell
 GridArgs main_grid_args(kp_pipeline *pl, EngSlot &s, int level, const float *xyz, DCnt n, double cell)
 {
     const int64_t NPs = pl->NPr;                                 // row stride of every main-branch array
@@ -964,8 +1207,8 @@ GridArgs main_grid_args(kp_pipeline *pl, EngSlot &s, int level, const float *xyz
     memset(&a, 0, sizeof a);
     a.g = &s.dyn->g[level]; a.g_stride = sizeof(EngDyn);
     a.xyz = xyz; a.xyz_stride = NPs; a.n = n;
-    if (level == 0) { a.b6 = s.dyn->b6; a.b6_stride = sizeof(EngDyn) / 4; a.parent = nullptr; a.parent_mult = 1.0; a.cell = cell; }
-    else { a.b6 = nullptr; a.parent = &s.dyn->g[0]; a.parent_mult = 3.0; a.cell = 0.0; }
+    a.b6 = s.dyn->b6; a.b6_stride = sizeof(EngDyn) / 4; a.parent = nullptr; a.parent_mult = 1.0;
+    a.cell = level == 0 ? cell / (double)pl->knn_rad : 3.0 * cell;
     a.sorted = s.sorted[level]; a.sorted_stride = NPs;
     a.cellmap = s.cellmap[level]; a.map_stride = pl->cap_cells / 32 + 64;
     a.cell_cnt = s.cell_cnt[level]; a.cnt_stride = NPs + 64;
@@ -975,23 +1218,36 @@ GridArgs main_grid_args(kp_pipeline *pl, EngSlot &s, int level, const float *xyz
     return a;
 }
 
-// ---- stage: remove_statistical_outlier of the batch's clouds `in` (n rows each) -> `out`, n_out
-int stage_sor(kp_pipeline *pl, EngSlot &s, int use, const float *in, DCnt n, int k, double ratio, float *out, DOut n_out)
+// ---- stage: remove_statistical_outlier of the batch's clouds `in` (n rows each, voxel coordinates vin) -> `out`, n_out
+int stage_sor(kp_pipeline *pl, EngSlot &s, int use, const float *in, const uint32_t *vin, DCnt n, int k, double ratio, float *out,
+              uint32_t *vout, DOut n_out)
 {
     kp_ctx *ctx = s.ctx;
     const int B = pl->B;
     const int64_t NPs = pl->NPr;
     KP_PROF(ctx, use == 0 ? "sor" : "floor_sor");
-    GridArgs g0 = main_grid_args(pl, s, 0, in, n, kp_knn_cell_from_voxel(pl->cfg.voxel_size, k));
-    KP_TRY(stage_grid(pl, ctx, g0, B, NPs, s.scan, dout(s.sink, 4)));
+    const double cell = kp_knn_cell_from_voxel(pl->cfg.voxel_size, k);
     KnnStage ks;
     ks.batch = use == 0 ? &s.knn_sor : &s.knn_fsor;
-    ks.coarse = main_grid_args(pl, s, 1, in, n, 0.0);
+    ks.vbi = pl->use_vbi_knn;
+    memset(&ks.vbi_args, 0, sizeof ks.vbi_args);
+    if (ks.vbi) {
+        VbiArgs &v = ks.vbi_args;
+        v.v = &s.dyn->vbi[0]; v.v_stride = sizeof(EngDyn);
+        v.xyz = in; v.xyz_stride = NPs; v.vijk = vin; v.vijk_stride = NPs; v.n = n;
+        v.vp = &s.dyn->vox_fused; v.vp_stride = sizeof(EngDyn);
+        v.bricks = s.bricks; v.brick_stride = pl->cap_bricks; v.cap_bricks = pl->cap_bricks;
+        v.pts = s.sorted[0]; v.vijk_sorted = s.vsorted; v.pts_stride = NPs;      // the index's rows ARE the level-0 rows of levels 1 / 2
+        v.status = &s.dyn->status; v.status_stride = sizeof(EngDyn) / 4;
+    }
+    ks.n_old = DYN_OUT(s, n_old[use]);
+    ks.fine = main_grid_args(pl, s, 0, in, ks.vbi ? DYN_CNT(s, n_old[use]) : n, cell);
+    ks.coarse = main_grid_args(pl, s, 1, in, n, cell);
     ks.flags0 = s.flags[0]; ks.flags1 = s.flags[1]; ks.flag_stride = NPs;
     ks.list0 = s.list[0]; ks.list1 = s.list[1]; ks.list_stride = NPs;
     ks.cnt0 = DYN_OUT(s, cnt_l0[use]); ks.cnt1 = DYN_OUT(s, cnt_l1[use]);
     ks.n = n;
-    KP_TRY(stage_knn(pl, ctx, ks, B, NPs, s.scan, dout(s.sink, 4)));
+    KP_TRY(stage_knn(pl, ctx, ks, B, NPs, s.scan, dout(s.sink, 4), true));
     {
         KP_PROFB(ctx, "sor_stats", 0.0);
         BLaunch L{ctx, B, NPs, ctas_for(pl, 4)};
@@ -1003,11 +1259,11 @@ int stage_sor(kp_pipeline *pl, EngSlot &s, int use, const float *in, DCnt n, int
         KP_LAUNCH_CHECK(ctx);
     }
     BLaunch L{ctx, B, NPs, ctas_for(pl, 4)};
-    return kp_b_compact_rows(L, s.scan, n, s.mask, NPs, 0, in, out, NPs, n_out);
+    return kp_b_compact_rows(L, s.scan, n, s.mask, NPs, 0, in, out, NPs, n_out, vout ? vin : nullptr, vout);
 }
 
 // ---- stage: floor removal (band split, RANSAC plane on the band, band outliers + upper part)
-int stage_floor(kp_pipeline *pl, EngSlot &s, const float *in)
+int stage_floor(kp_pipeline *pl, EngSlot &s, const float *in, const uint32_t *vin)
 {
     kp_ctx *ctx = s.ctx;
     const kp_pipeline_cfg &c = pl->cfg;
@@ -1024,7 +1280,7 @@ int stage_floor(kp_pipeline *pl, EngSlot &s, const float *in)
         KP_LAUNCH_CHECK(ctx);
     }
     // lower band -> C, upper part -> D
-    KP_TRY(kp_b_partition_rows(L, s.scan, DYN_CNT(s, n_sor), s.mask, NPs, in, s.C, s.D, NPs, DYN_OUT(s, n_lo)));
+    KP_TRY(kp_b_partition_rows(L, s.scan, DYN_CNT(s, n_sor), s.mask, NPs, in, s.C, s.D, NPs, DYN_OUT(s, n_lo), vin, s.vC, s.vD));
     {
         DeriveArgs d{s.dyn, s.n_up, c.do_floor, c.floor_sor_k > 0};
         k_e_derive_up<<<kp_blocks(B, 64), 64, 0, ctx->stream>>>(d, B);
@@ -1059,10 +1315,10 @@ int stage_floor(kp_pipeline *pl, EngSlot &s, const float *in)
         KP_LAUNCH_CHECK(ctx);
     }
     // outlier_cloud + upper (floor_removal.py:71-72): band outliers first, then the upper part
-    KP_TRY(kp_b_compact_rows(L, s.scan, DYN_CNT(s, n_lo), s.mask2, NPs, 1, s.C, s.E, NPs, DYN_OUT(s, n_rest)));
+    KP_TRY(kp_b_compact_rows(L, s.scan, DYN_CNT(s, n_lo), s.mask2, NPs, 1, s.C, s.E, NPs, DYN_OUT(s, n_rest), vin ? s.vC : nullptr, s.vE));
     {
         KP_PROFB(ctx, "merge", 0.0);
-        AppendArgs a{s.D, s.E, NPs, DCnt{s.n_up, 1}, DYN_CNT(s, n_rest), DYN_OUT(s, n_merged)};
+        AppendArgs a{s.D, s.E, NPs, DCnt{s.n_up, 1}, DYN_CNT(s, n_rest), DYN_OUT(s, n_merged), vin ? s.vD : nullptr, s.vE};
         k_e_append_rows<<<grid, 256, 0, ctx->stream>>>(a);
         KP_LAUNCH_CHECK(ctx);
     }
@@ -1080,35 +1336,49 @@ int stage_icp(kp_pipeline *pl, EngSlot &s, kp_ctx *ctx)
     const DCnt nv = dcnt(&s.icl->nv, sizeof(EngCloud));
     const DOut nvox = dout(&s.icl->n, sizeof(EngCloud));
     KP_TRY(stage_voxel(pl, ctx, B * S, P, s.icp_in, P, &s.icl->vox, sizeof(EngCloud), nv, s.ikeys, s.ikeys_tmp, s.ivals, s.ivals_tmp, Pr,
-                       s.isortw, s.iscan, s.irun_start, Pr + 64, s.ivox, Pr, nvox));
-    // target grid (cell covers both the normals radius and the ICP gate) over the master's voxel cloud
+                       s.isortw, s.iscan, s.irun_start, Pr + 64, s.ivox, Pr, nvox, s.ivijk));
+    // voxel-brick index over every frame's target (the master's voxel cloud): normals and ICP correspondences search it;
+    // the grid is the fallback for a target whose index could not be built (n_old = its points then, else 0)
     const DCnt ntgt = dcnt(&s.icl->n, sizeof(EngCloud) * S);
+    KnnStage ks;
+    ks.batch = &s.knn_nrm;
+    ks.vbi = pl->use_vbi_icp;
+    memset(&ks.vbi_args, 0, sizeof ks.vbi_args);
+    if (ks.vbi) {
+        VbiArgs &v = ks.vbi_args;
+        v.v = &s.dyn->vbi[1]; v.v_stride = sizeof(EngDyn);
+        v.xyz = s.ivox; v.xyz_stride = (int64_t)S * Pr; v.vijk = s.ivijk; v.vijk_stride = (int64_t)S * Pr;
+        v.n = ntgt;
+        v.vp = &s.icl->vox; v.vp_stride = sizeof(EngCloud) * S;
+        v.bricks = s.ibricks; v.brick_stride = pl->cap_bricks; v.cap_bricks = pl->cap_bricks;
+        v.pts = s.isorted[0]; v.vijk_sorted = s.ivijk_sorted; v.pts_stride = Pr;
+        v.status = &s.dyn->status; v.status_stride = sizeof(EngDyn) / 4;
+    }
+    ks.n_old = DYN_OUT(s, n_old[2]);
     GridArgs g;
     memset(&g, 0, sizeof g);
     g.g = &s.dyn->g[2]; g.g_stride = sizeof(EngDyn);
-    g.xyz = s.ivox; g.xyz_stride = (int64_t)S * Pr; g.n = ntgt;
+    g.xyz = s.ivox; g.xyz_stride = (int64_t)S * Pr; g.n = ks.vbi ? DYN_CNT(s, n_old[2]) : ntgt;
     g.b6 = s.icl->b6; g.b6_stride = sizeof(EngCloud) * S / 4; g.parent = nullptr; g.parent_mult = 1.0;
-    g.cell = fmax(c.normals_radius * (1.0 + 4e-6), c.icp_max_corr * (1.0 + 1e-6));
+    g.cell = fmax(c.normals_radius * (1.0 + 4e-6), c.icp_max_corr * (1.0 + 1e-6));      // covers the normals radius and the ICP gate
     g.sorted = s.isorted[0]; g.sorted_stride = Pr;
     g.cellmap = s.icellmap[0]; g.map_stride = pl->cap_cells / 32 + 64;
     g.cell_cnt = s.icell_cnt[0]; g.cnt_stride = Pr + 64;
     g.rank = s.ig_rank; g.loc = s.ig_loc; g.tmp_stride = Pr;
     g.cap_cells = pl->cap_cells;
     g.nocc = DYN_OUT(s, nocc[2]);
-    KP_TRY(stage_grid(pl, ctx, g, B, Pr, s.iscan, dout(s.isink, 4)));
+    ks.fine = g;
+    ks.coarse = g;
+    ks.coarse.g = &s.dyn->g[3]; ks.coarse.n = ntgt; ks.coarse.cell = 3.0 * g.cell;
+    ks.coarse.sorted = s.isorted[1]; ks.coarse.cellmap = s.icellmap[1]; ks.coarse.cell_cnt = s.icell_cnt[1];
+    ks.coarse.nocc = DYN_OUT(s, nocc[3]);
+    ks.flags0 = s.iflags[0]; ks.flags1 = s.iflags[1]; ks.flag_stride = Pr;
+    ks.list0 = s.ilist[0]; ks.list1 = s.ilist[1]; ks.list_stride = Pr;
+    ks.cnt0 = DYN_OUT(s, cnt_l0[2]); ks.cnt1 = DYN_OUT(s, cnt_l1[2]);
+    ks.n = ntgt;
     {
         KP_PROF(ctx, "normals");
-        KnnStage ks;
-        ks.batch = &s.knn_nrm;
-        ks.coarse = g;
-        ks.coarse.g = &s.dyn->g[3]; ks.coarse.b6 = nullptr; ks.coarse.parent = &s.dyn->g[2]; ks.coarse.parent_mult = 3.0; ks.coarse.cell = 0.0;
-        ks.coarse.sorted = s.isorted[1]; ks.coarse.cellmap = s.icellmap[1]; ks.coarse.cell_cnt = s.icell_cnt[1];
-        ks.coarse.nocc = DYN_OUT(s, nocc[3]);
-        ks.flags0 = s.iflags[0]; ks.flags1 = s.iflags[1]; ks.flag_stride = Pr;
-        ks.list0 = s.ilist[0]; ks.list1 = s.ilist[1]; ks.list_stride = Pr;
-        ks.cnt0 = DYN_OUT(s, cnt_l0[2]); ks.cnt1 = DYN_OUT(s, cnt_l1[2]);
-        ks.n = ntgt;
-        KP_TRY(stage_knn(pl, ctx, ks, B, Pr, s.iscan, dout(s.isink, 4)));
+        KP_TRY(stage_knn(pl, ctx, ks, B, Pr, s.iscan, dout(s.isink, 4), true));
     }
     return kp_icp_batch_run(ctx, s.icp);
 }
@@ -1147,7 +1417,9 @@ int slot_create(kp_pipeline *pl, EngSlot &s)
     SA(s.sortw.g_hist, (size_t)B * kp_b_sort_hist_elems(NP)); SA(s.sortw.g_tot, B * 256);
     const int64_t word_tiles = (pl->cap_cells / 32 + 1 + BC_TILE - 1) / BC_TILE;
     const int64_t row_tiles = (NPr + 66 + BC_TILE - 1) / BC_TILE;
+    const int64_t brick_tiles = (pl->cap_bricks + BC_TILE - 1) / BC_TILE;
     s.scan.max_tiles = (int)((word_tiles > row_tiles ? word_tiles : row_tiles) + 1);
+    if (s.scan.max_tiles < brick_tiles + 1) s.scan.max_tiles = (int)brick_tiles + 1;
     SA(s.scan.tile_sum, (size_t)B * s.scan.max_tiles); SAZ(s.scan.ticket, B);
     SA(s.A, B * NPr * 3); SA(s.Bb, B * NPr * 3); SA(s.C, B * NPr * 3); SA(s.D, B * NPr * 3); SA(s.E, B * NPr * 3); SA(s.Fin, B * NPr * 3);
     const int64_t map_stride = pl->cap_cells / 32 + 64;
@@ -1159,6 +1431,10 @@ int slot_create(kp_pipeline *pl, EngSlot &s)
     SA(s.mean, B * NPr); SA(s.csum_tmp, B * (NPr / 1024 + NPr / 1048576 + 16));
     SA(s.mask, B * NPr); SA(s.mask2, B * NPr);
     SAZ(s.n_up, B); SAZ(s.sink, B);
+    if (pl->use_vbi_knn) {
+        SA(s.vA, B * NPr); SA(s.vB, B * NPr); SA(s.vC, B * NPr); SA(s.vD, B * NPr); SA(s.vE, B * NPr); SA(s.vsorted, B * NPr);
+        SA(s.bricks, (size_t)B * pl->cap_bricks);
+    }
     const int iters = c.ransac_iters > 0 ? c.ransac_iters : 1;
     SA(s.planes, (size_t)B * iters); SA(s.pvalid, (size_t)B * iters); SA(s.hcnt, (size_t)B * iters);
     SA(s.tie_slots, (size_t)B * ENG_MAX_CAND * pl->sm_count * 2);
@@ -1170,14 +1446,18 @@ int slot_create(kp_pipeline *pl, EngSlot &s)
             KpKnnSegDesc &e = d[b];
             memset(&e, 0, sizeof e);
             e.g0 = &s.dyn[b].g[0]; e.g1 = &s.dyn[b].g[1];
+            e.vbi = pl->use_vbi_knn ? &s.dyn[b].vbi[0] : nullptr;
             e.pts0 = s.sorted[0] + (size_t)b * NPr;
-            e.n = use == 0 ? &s.dyn[b].n_voxel : &s.dyn[b].n_merged;
+            e.n = pl->use_vbi_knn ? &s.dyn[b].n_old[use] : (use == 0 ? &s.dyn[b].n_voxel : &s.dyn[b].n_merged);
             e.flags0 = s.flags[0] + (size_t)b * NPr; e.flags1 = s.flags[1] + (size_t)b * NPr;
             e.list0 = s.list[0] + (size_t)b * NPr; e.list1 = s.list[1] + (size_t)b * NPr;
             e.cnt0 = &s.dyn[b].cnt_l0[use]; e.cnt1 = &s.dyn[b].cnt_l1[use];
             e.mean = s.mean + (size_t)b * NPr;
         }
-        rc = kp_knn_batch_create(s.ctx, d.data(), B, k, 0, 0.0, use == 0 ? &s.knn_sor : &s.knn_fsor);
+        // voxel-brick level 0: rho_a certifies the dense parts of the cloud, rho_b the sparse ones (multiples of the radius
+        // that holds k points of a one-point-per-voxel surface)
+        const double rk = c.voxel_size * sqrt((double)k / 3.14159265358979);
+        rc = kp_knn_batch_create(s.ctx, d.data(), B, k, 0, 0.0, pl->rho_mult_a * rk, pl->rho_mult_b * rk, use == 0 ? &s.knn_sor : &s.knn_fsor);
         if (rc != KP_OK) { pl->err = s.ctx->err; return rc; }
     }
     if (icp) {
@@ -1187,6 +1467,7 @@ int slot_create(kp_pipeline *pl, EngSlot &s)
         SA(s.isortw.g_hist, (size_t)B * S * kp_b_sort_hist_elems(P)); SA(s.isortw.g_tot, (size_t)B * S * 256);
         const int64_t irow_tiles = (Pr + 66 + BC_TILE - 1) / BC_TILE;
         s.iscan.max_tiles = (int)((word_tiles > irow_tiles ? word_tiles : irow_tiles) + 1);
+        if (s.iscan.max_tiles < brick_tiles + 1) s.iscan.max_tiles = (int)brick_tiles + 1;
         SA(s.iscan.tile_sum, (size_t)B * S * s.iscan.max_tiles); SAZ(s.iscan.ticket, (size_t)B * S);
         SA(s.ivox, (size_t)B * S * Pr * 3);
         for (int l = 0; l < 2; ++l) {
@@ -1195,26 +1476,30 @@ int slot_create(kp_pipeline *pl, EngSlot &s)
         }
         SA(s.ig_rank, B * Pr); SA(s.ig_loc, B * Pr);
         SA(s.nrm, B * Pr * 3);
+        SA(s.ivijk, (size_t)B * S * Pr); SA(s.ivijk_sorted, B * Pr); SA(s.ibricks, (size_t)B * pl->cap_bricks);
         SAZ(s.isink, (size_t)B * S);
         for (int b = 0; b < B; ++b) {
             KpKnnSegDesc &e = d[b];
             memset(&e, 0, sizeof e);
             e.g0 = &s.dyn[b].g[2]; e.g1 = &s.dyn[b].g[3];
+            e.vbi = pl->use_vbi_icp ? &s.dyn[b].vbi[1] : nullptr;
             e.pts0 = s.isorted[0] + (size_t)b * Pr;
-            e.n = &s.icl[(size_t)b * S].n;
+            e.n = pl->use_vbi_icp ? &s.dyn[b].n_old[2] : &s.icl[(size_t)b * S].n;
             e.flags0 = s.iflags[0] + (size_t)b * Pr; e.flags1 = s.iflags[1] + (size_t)b * Pr;
             e.list0 = s.ilist[0] + (size_t)b * Pr; e.list1 = s.ilist[1] + (size_t)b * Pr;
             e.cnt0 = &s.dyn[b].cnt_l0[2]; e.cnt1 = &s.dyn[b].cnt_l1[2];
             e.cloud = s.ivox + 3 * (size_t)b * S * Pr;
             e.normals = s.nrm + 3 * (size_t)b * Pr;
         }
-        rc = kp_knn_batch_create(s.ctx, d.data(), B, c.normals_max_nn, 1, c.normals_radius, &s.knn_nrm);
+        rc = kp_knn_batch_create(s.ctx, d.data(), B, c.normals_max_nn, 1, c.normals_radius, c.normals_radius * 1.001, c.normals_radius * 1.001,
+                                 &s.knn_nrm);
         if (rc != KP_OK) { pl->err = s.ctx->err; return rc; }
         std::vector<KpIcpPairDesc> pr;
         for (int b = 0; b < B; ++b)
             for (int sn = 1; sn < S && sn <= 5; ++sn) {
                 KpIcpPairDesc e;
                 e.tgt_grid = &s.dyn[b].g[2];
+                e.tgt_vbi = pl->use_vbi_icp ? &s.dyn[b].vbi[1] : nullptr;
                 e.tgt_normals = s.nrm + 3 * (size_t)b * Pr;
                 e.src = s.ivox + 3 * ((size_t)b * S + sn) * Pr;
                 e.n_src = &s.icl[(size_t)b * S + sn].n;
@@ -1270,20 +1555,22 @@ int enqueue_core(kp_pipeline *pl, EngSlot &s, bool fork)
     if (icp && fork) KP_TRY(stage_icp(pl, s, ictx));      // enqueued first so that its small kernels interleave with the main branch
     // ---- filter_outliers: voxel + SOR
     KP_TRY(stage_voxel(pl, ctx, B, NP, s.fused, NP, &s.dyn->vox_fused, sizeof(EngDyn), DYN_CNT(s, n_fused), s.keys, s.keys_tmp, s.vals,
-                       s.vals_tmp, NPr, s.sortw, s.scan, s.run_start, NPr + 64, s.A, NPr, DYN_OUT(s, n_voxel)));
+                       s.vals_tmp, NPr, s.sortw, s.scan, s.run_start, NPr + 64, s.A, NPr, DYN_OUT(s, n_voxel), s.vA));
     const float *sor_out = s.A;
+    const uint32_t *v_sor_out = s.vA;
     if (c.sor_k > 0) {
-        KP_TRY(stage_sor(pl, s, 0, s.A, DYN_CNT(s, n_voxel), c.sor_k, c.sor_ratio, s.Bb, DYN_OUT(s, n_sor)));
+        KP_TRY(stage_sor(pl, s, 0, s.A, s.vA, DYN_CNT(s, n_voxel), c.sor_k, c.sor_ratio, s.Bb, s.vB, DYN_OUT(s, n_sor)));
         sor_out = s.Bb;
+        v_sor_out = s.vB;
     } else {
         k_e_copy_cnt<<<kp_blocks(B, 64), 64, 0, ctx->stream>>>(DYN_CNT(s, n_voxel), DYN_OUT(s, n_sor), B);
         KP_LAUNCH_CHECK(ctx);
     }
     // ---- floor removal + SOR
     if (c.do_floor) {
-        KP_TRY(stage_floor(pl, s, sor_out));
+        KP_TRY(stage_floor(pl, s, sor_out, v_sor_out));
         if (c.floor_sor_k > 0)
-            KP_TRY(stage_sor(pl, s, 1, s.E, DYN_CNT(s, n_merged), c.floor_sor_k, c.floor_sor_ratio, s.Fin, DYN_OUT(s, n_fsor)));
+            KP_TRY(stage_sor(pl, s, 1, s.E, s.vE, DYN_CNT(s, n_merged), c.floor_sor_k, c.floor_sor_ratio, s.Fin, nullptr, DYN_OUT(s, n_fsor)));
     }
     if (icp && !fork) KP_TRY(stage_icp(pl, s, ctx));
     if (icp && fork) {
@@ -1305,7 +1592,7 @@ int slot_capture(kp_pipeline *pl, EngSlot &s)
     PL_CUDA(pl, cudaStreamBeginCapture(s.ctx->stream, cudaStreamCaptureModeThreadLocal));
     int rc = enqueue_core(pl, s, true);
     cudaError_t e = cudaStreamEndCapture(s.ctx->stream, &g);
-    if (rc != KP_OK) { pl->err = s.ctx->err; if (g) cudaGraphDestroy(g); return rc; }
+    if (rc != KP_OK) { pl->err = s.ctx->err.empty() ? s.aux->err : s.ctx->err; if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) { pl->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return KP_E_CUDA; }
     e = cudaGraphInstantiate(&s.graph, g, 0);
     cudaGraphDestroy(g);
@@ -1350,7 +1637,7 @@ int run_impl(kp_pipeline *p, const uint16_t *depth, int depth_on_device, int64_t
         if (rc != KP_OK) { p->err = ctx->err; return rc; }
         if (direct) {
             rc = enqueue_core(p, s, !p->profiling);
-            if (rc != KP_OK) { p->err = ctx->err; return rc; }
+            if (rc != KP_OK) { p->err = ctx->err.empty() ? s.aux->err : ctx->err; return rc; }
         } else {
             PL_CUDA(p, cudaGraphLaunch(s.graph, ctx->stream));
             p->launches += s.graph_nodes;
@@ -1370,6 +1657,13 @@ int run_impl(kp_pipeline *p, const uint16_t *depth, int depth_on_device, int64_t
         PL_CUDA(p, cudaStreamSynchronize(p->slots[w].aux->stream));
     }
     memcpy(h_results, p->h_res, sizeof(kp_frame_result) * (size_t)F);
+    if (getenv("KP_PIPE_DEBUG")) {
+        EngDyn d;
+        cudaMemcpy(&d, p->slots[0].dyn, sizeof d, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[kp engine] frame 0 of slot 0: fused %d voxel %d sor %d lo %d rest %d merged %d fsor %d | leftovers L0 %d %d %d  L1 %d %d %d | cells %d %d %d %d | g0 cell %g dims %d %d %d\n",
+                d.n_fused, d.n_voxel, d.n_sor, d.n_lo, d.n_rest, d.n_merged, d.n_fsor, d.cnt_l0[0], d.cnt_l0[1], d.cnt_l0[2], d.cnt_l1[0],
+                d.cnt_l1[1], d.cnt_l1[2], d.nocc[0], d.nocc[1], d.nocc[2], d.nocc[3], d.g[0].cell, d.g[0].dim[0], d.g[0].dim[1], d.g[0].dim[2]);
+    }
     for (int64_t f = 0; f < F; ++f)
         if (h_results[f].status != KP_OK) {
             char buf[160];
@@ -1418,11 +1712,19 @@ int kp_pipeline_create(int device, const kp_pipeline_cfg *cfg, const float *h_xy
     if (W > 8) W = 8;
     p->B = B; p->W = W;
     p->use_graph = !(getenv("KP_PIPE_GRAPH") && atoi(getenv("KP_PIPE_GRAPH")) == 0);
+    p->use_vbi_icp = getenv("KP_ICP_VBI") && atoi(getenv("KP_ICP_VBI")) != 0;   // 8 % fewer ICP pass time, paid back by the index build: off unless asked for
+    p->use_vbi_knn = getenv("KP_KNN_VBI") && atoi(getenv("KP_KNN_VBI")) != 0;   // measured slower than the grid level 0: off unless asked for
+    p->knn_rad = (getenv("KP_KNN_RAD") && atoi(getenv("KP_KNN_RAD")) == 2) ? 2 : 1;
+    if (getenv("KP_VBI_RHO_A")) p->rho_mult_a = atof(getenv("KP_VBI_RHO_A"));
+    if (getenv("KP_VBI_RHO_B")) p->rho_mult_b = atof(getenv("KP_VBI_RHO_B"));
     const int S = cfg->S;
     const size_t NP = (size_t)S * cfg->P;
     int64_t cells = 1 << 20;
     while (cells < (int64_t)NP * 16 && cells < (1 << 25)) cells <<= 1;
     p->cap_cells = cells;
+    int64_t bricks = 1 << 16;
+    while (bricks < (int64_t)NP * 3 && bricks < (1 << 23)) bricks <<= 1;
+    p->cap_bricks = bricks;
     p->NPr = ((int64_t)NP + 63) & ~(int64_t)63;
     p->Pr = (cfg->P + 63) & ~(int64_t)63;
     p->T_fuse.assign(16 * S, 0.0);
@@ -1451,7 +1753,7 @@ int kp_pipeline_create(int device, const kp_pipeline_cfg *cfg, const float *h_xy
         int rc = kp_unproject_engine(s.ctx, s.d_depth, p->d_tab, p->T_fuse.data(), B, S, cfg->P, cfg->unproject_flags, cfg->scale, s.fused,
                                      (cfg->do_icp && S > 1) ? s.icp_in : nullptr, s.k1_slots, s.k1_rows);
         if (rc == KP_OK) rc = enqueue_core(p, s, true);
-        if (rc != KP_OK) { p->err = s.ctx->err; return fail(rc); }
+        if (rc != KP_OK) { p->err = s.ctx->err.empty() ? s.aux->err : s.ctx->err; return fail(rc); }
         if (cudaStreamSynchronize(s.ctx->stream) != cudaSuccess || cudaStreamSynchronize(s.aux->stream) != cudaSuccess) {
             p->err = std::string("warm-up pass failed: ") + cudaGetErrorString(cudaGetLastError());
             return fail(KP_E_CUDA);

@@ -272,25 +272,18 @@ struct KnnParams {
     // frame engine (batched launches, kp_engine.cu): the grid layout and the query count were produced on the device
     const KpGridDev *gdev;                         // non-NULL: replaces g
     const int32_t *nq_dev;                         // non-NULL: replaces nq
+    const KpVbiDev *vbi;                           // voxel-brick index of the cloud (k_knn_vbi_b)
+    double rho_a, rho_b;                           // its two search radii
 };
 
-// batched launches read their parameter block from device memory (blockIdx.y selects the frame): the block is
-// copied to shared memory once per CTA and the device-side grid layout / query count are patched in
-__device__ __forceinline__ const KnnParams &knn_params_batched(const KnnParams *pp)
+// batched launches read their parameter block from device memory (blockIdx.y selects the frame): uniform, cached
+// loads of the fields a thread uses, with the device-side grid layout / query count patched in
+__device__ __forceinline__ KnnParams knn_params_batched(const KnnParams *__restrict__ pp)
 {
-    __shared__ KnnParams s_p;
-    const int *src = reinterpret_cast<const int *>(pp + blockIdx.y);
-    int *dst = reinterpret_cast<int *>(&s_p);
-    for (int i = threadIdx.x; i < (int)(sizeof(KnnParams) / 4); i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-    if (s_p.gdev) {
-        const int *gs = reinterpret_cast<const int *>(s_p.gdev);
-        int *gd = reinterpret_cast<int *>(&s_p.g);
-        for (int i = threadIdx.x; i < (int)(sizeof(KpGridDev) / 4); i += blockDim.x) gd[i] = gs[i];
-    }
-    if (threadIdx.x == 0 && s_p.nq_dev) s_p.nq = *s_p.nq_dev;
-    __syncthreads();
-    return s_p;
+    KnnParams p = pp[blockIdx.y];
+    if (p.gdev) p.g = *p.gdev;
+    if (p.nq_dev) p.nq = *p.nq_dev;
+    return p;
 }
 
 __device__ __forceinline__ bool kq_less(double d, int i, double td, int ti) { return d < td || (d == td && i < ti); }
@@ -694,7 +687,8 @@ __global__ void __launch_bounds__(KQ_WARPS * 32) k_knn(const __grid_constant__ K
 __global__ void __launch_bounds__(KQ_WARPS * 32) k_knn_b(const KnnParams *pp)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    knn_warp_body(knn_params_batched(pp), smem_raw);
+    const KnnParams p = knn_params_batched(pp);      // thread-local copy: the loops read registers, not shared memory
+    knn_warp_body(p, smem_raw);
 }
 
 // ---- histogram-select kernels (the fast path: k <= HQ_KMAX, the cloud queries itself).
@@ -807,9 +801,8 @@ __device__ void kq_finish_normal(const KnnParams &p, int64_t row, int cnt, doubl
 }
 
 template <int NB, int R, int HQT>
-__device__ __forceinline__ void hq_query(const KnnParams &p, const int64_t q, unsigned char *smem_raw)
+__device__ __forceinline__ void hq_query(const KnnParams &p, const KpGridDev &g, const int64_t q, unsigned char *smem_raw)
 {
-    const KpGridDev &g = p.g;
     const int tid = threadIdx.x;
     // buf[slot * HQT], hist[bin * HQT]: any slot pattern is bank-conflict free
     unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem_raw) + tid;
@@ -997,14 +990,157 @@ __global__ void __launch_bounds__(HQT) k_knn_hist(const __grid_constant__ KnnPar
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int64_t w = (int64_t)blockIdx.x * HQT + threadIdx.x;
     if (w >= p.nq) return;
-    hq_query<NB, R, HQT>(p, w, smem_raw);
+    hq_query<NB, R, HQT>(p, p.g, w, smem_raw);
 }
+// batched form: the parameter blocks of up to KNN_ARG_SEGS segments travel BY VALUE (constant bank: the hot loops read
+// k, cap, the pointers ... as instruction operands, as in the single-cloud kernel); only the grid layout and the query
+// count, which an earlier kernel of the frame produced, are loaded from device memory into registers
+constexpr int KNN_ARG_SEGS = 8;
+struct KnnBatchArgs { KnnParams p[KNN_ARG_SEGS]; };
 template <int NB, int R, int HQT>
-__global__ void __launch_bounds__(HQT) k_knn_hist_b(const KnnParams *pp)
+__global__ void __launch_bounds__(HQT) k_knn_hist_b(const __grid_constant__ KnnBatchArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const KnnParams &p = knn_params_batched(pp);
-    for (int64_t w = (int64_t)blockIdx.x * HQT + threadIdx.x; w < p.nq; w += (int64_t)gridDim.x * HQT) hq_query<NB, R, HQT>(p, w, smem_raw);
+    const KnnParams &p = a.p[blockIdx.y];
+    const KpGridDev g = *p.gdev;
+    const int64_t nq = *p.nq_dev;
+    for (int64_t w = (int64_t)blockIdx.x * HQT + threadIdx.x; w < nq; w += (int64_t)gridDim.x * HQT) hq_query<NB, R, HQT>(p, g, w, smem_raw);
+}
+
+// ---- the same histogram select over the voxel-brick index (kp_vbi.cuh) of a voxel-downsampled cloud.
+// The candidates of a query are the occupied voxels inside the voxel box of the ball of radius rho around it:
+// per brick one 16-byte load and an AND with the box mask; there are no cell runs to look up and a voxel holds one
+// point, so a query reads about a third of the points the 27-cell block of the grid kernel holds.  Two radii: rho_a
+// certifies the dense parts of the cloud, rho_b (a wider box, restarted from scratch) the sparse ones; what neither
+// certifies goes to level 1 like the grid kernel's leftovers.  Selection, exact evaluation in double and the
+// certificate are those of hq_query.
+template <int NB, int HQT>
+__device__ __forceinline__ void vq_query(const KnnParams &p, const KpVbiDev &v, const int64_t q, unsigned char *smem_raw)
+{
+    const int tid = threadIdx.x;
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem_raw) + tid;
+    unsigned short *hist = reinterpret_cast<unsigned short *>(smem_raw + (size_t)p.cap * HQT * sizeof(unsigned long long)) + tid;
+    const int k = p.k;
+    const float4 me = __ldg(v.pts + q);
+    const int64_t row = __float_as_int(me.w);
+    const double qx = (double)me.x, qy = (double)me.y, qz = (double)me.z;
+    const bool capped = p.r2cap > 0;
+    const bool normals = p.mode == KQ_MODE_NORMALS;
+    for (int phase = 0; phase < 2; ++phase) {
+        const double rho = phase == 0 ? p.rho_a : p.rho_b;
+        double R2 = rho * rho;
+        bool cap_binding = false;
+        if (capped) {
+            const double capw = p.r2cap * (1.0 + 2e-6);          // every candidate with d2 < r2cap has fp32 d2 < capw
+            if (capw <= R2) { R2 = capw; cap_binding = true; }
+        }
+        // voxel box of the ball: every point with d2 <= R2 sits in a voxel of it (eps: float32 rounding of the stored means)
+        const double rad = sqrt(R2) * (1.0 + 1e-6) + v.eps + v.voxel * 1e-6;
+        KpVbiBox box;
+        kp_vbi_box(v, qx, qy, qz, rad, box);
+        const float scale = (float)((double)(NB - 1) / R2);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) hist[j * HQT] = 0;
+        kp_vbi_visit(v, box, [&](int, const float4 &c) {
+            const int bj = hq_bin(hq_d32(me.x, me.y, me.z, c), scale);
+            if ((unsigned)bj < (unsigned)NB) hist[bj * HQT]++;
+        });
+        int b = -1, m = 0;
+        {
+            int cum = 0;
+            for (int j = 0; j < NB; ++j) {
+                const int c = (int)hist[j * HQT];
+                hist[j * HQT] = (unsigned short)cum;
+                cum += c;
+                if (cum >= k) { b = j; break; }
+            }
+            m = cum;
+        }
+        const bool all = b < 0;                       // fewer than k in range: the loop ran over every bin, take them all
+        if (b < 0) b = NB - 1;
+        if (m > p.cap) { p.strag_flags[q] = 1; return; }
+        if (m < k && !cap_binding) {
+            if (phase == 0) continue;
+            p.strag_flags[q] = 1;
+            return;
+        }
+        int nput = 0;
+        // the collection pass only needs the box of the bins it takes (bins <= b end at fp32 d2 (b + 0.5) / scale)
+        kp_vbi_box(v, qx, qy, qz, sqrt(fmin(R2, ((double)b + 1.0) / (double)scale)) * (1.0 + 1e-5) + v.eps + v.voxel * 1e-6, box);
+        kp_vbi_visit(v, box, [&](int pos, const float4 &c) {
+            const float dj = hq_d32(me.x, me.y, me.z, c);
+            const int bu = hq_bin(dj, scale);
+            if ((unsigned)bu <= (unsigned)b) {
+                const int slot = hist[bu * HQT];
+                hist[bu * HQT] = (unsigned short)(slot + 1);
+                if (slot < m) buf[slot * HQT] = ((unsigned long long)__float_as_uint(dj) << 32) | (unsigned)pos;
+                ++nput;
+            }
+        });
+        if (nput != m) { p.strag_flags[q] = 1; return; }
+        // ---- order by (fp32 d2, position): entries only move inside their bin
+        for (int i = 1; i < m; ++i) {
+            const unsigned long long key = buf[i * HQT];
+            int j = i - 1;
+            while (j >= 0) {
+                const unsigned long long o = buf[j * HQT];
+                if (o <= key) break;
+                buf[(j + 1) * HQT] = o;
+                --j;
+            }
+            buf[(j + 1) * HQT] = key;
+        }
+        // ---- exact evaluation in that order; the canonical (d2, index) order must be strictly ascending
+        double pd = -1.0; int pi = -1;
+        double acc = 0.0;
+        double sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        int cnt = 0;
+        bool bad = false, closed = false;
+        float4 cn = m > 0 ? __ldg(v.pts + (unsigned)buf[0]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < m; ++i) {
+            const float4 c = cn;
+            if (i + 1 < m) cn = __ldg(v.pts + (unsigned)buf[(i + 1) * HQT]);
+            const double d = kp_d2(qx, qy, qz, (double)c.x, (double)c.y, (double)c.z);
+            const int id = __float_as_int(c.w);
+            if (!hq_before(pd, pi, d, id)) bad = true;
+            if (capped && !(d < p.r2cap)) closed = true;
+            if (cnt < k && !closed) {
+                pd = d; pi = id;
+                if (normals) {
+                    const double x = (double)c.x, y = (double)c.y, z = (double)c.z;
+                    sm[0] += x; sm[1] += y; sm[2] += z;
+                    sm[3] += x * x; sm[4] += x * y; sm[5] += x * z; sm[6] += y * y; sm[7] += y * z; sm[8] += z * z;
+                } else {
+                    acc = __dadd_rn(acc, sqrt(d));
+                }
+                ++cnt;
+            } else if (closed && d < p.r2cap) bad = true;
+        }
+        // exact iff nothing outside the collected set can precede the k-th entry: the visited-but-uncollected candidates
+        // lie above the lower edge of bin b+1, the unvisited ones (and the fp32-out-of-range ones) at or beyond the radius
+        bool exact;
+        if (all && cap_binding) exact = true;
+        else exact = cnt == k && pd < hq_lower_edge(b, scale) && (cap_binding || pd < R2 * (1.0 - 4e-6));
+        if (bad) { p.strag_flags[q] = 1; return; }
+        if (!exact) {
+            if (phase == 0 && !cap_binding) continue;
+            p.strag_flags[q] = 1;
+            return;
+        }
+        if (normals) { kq_finish_normal(p, row, cnt, sm); return; }
+        if (p.mean) p.mean[row] = cnt > 0 ? __ddiv_rn(acc, (double)cnt) : -1.0;
+        return;
+    }
+}
+template <int NB, int HQT>
+__global__ void __launch_bounds__(HQT, 512 / HQT) k_knn_vbi_b(const KnnParams *pp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const KnnParams p = knn_params_batched(pp);
+    if (!p.vbi) return;
+    const KpVbiDev v = *p.vbi;
+    if (!v.ok) return;
+    for (int64_t w = (int64_t)blockIdx.x * HQT + threadIdx.x; w < v.npts; w += (int64_t)gridDim.x * HQT) vq_query<NB, HQT>(p, v, w, smem_raw);
 }
 
 // ---- warp-per-query best-first histogram select: the level-0 stragglers (isolated points and sparse fringes
@@ -1245,7 +1381,11 @@ __device__ __forceinline__ void knn_wbf_body(const KnnParams &p)
     }
 }
 __global__ void __launch_bounds__(WH_WARPS * 32) k_knn_wbf(const __grid_constant__ KnnParams p) { knn_wbf_body(p); }
-__global__ void __launch_bounds__(WH_WARPS * 32) k_knn_wbf_b(const KnnParams *pp) { knn_wbf_body(knn_params_batched(pp)); }
+__global__ void __launch_bounds__(WH_WARPS * 32) k_knn_wbf_b(const KnnParams *pp)
+{
+    const KnnParams p = knn_params_batched(pp);
+    knn_wbf_body(p);
+}
 
 int next_pow2(int v)
 {
@@ -1492,9 +1632,11 @@ int kp_normals_device(kp_ctx *ctx, const float *d_xyz, int64_t n, double radius,
 // ---------------------------------------------------------------- frame engine: batched neighbour searches
 // One parameter block per (level, segment) lives in device memory, written once when the engine is created
 // (every pointer in it is static; grid layouts and counts are read through gdev / nq_dev / qcount at run time).
-int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, int mode, double radius, KpKnnBatch *out)
+int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, int mode, double radius, double rho_a, double rho_b,
+                        KpKnnBatch *out)
 {
     out->nseg = nseg; out->k = k; out->mode = mode;
+    out->rad = (getenv("KP_KNN_RAD") && atoi(getenv("KP_KNN_RAD")) == 2) ? 2 : 1;
     static const int slack = getenv("KP_KNN_SLACK") ? atoi(getenv("KP_KNN_SLACK")) : 8;
     out->cap_hist = k + slack;
     int capw = next_pow2(4 * k > 128 ? 4 * k : 128);
@@ -1506,13 +1648,14 @@ int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, 
         const KpKnnSegDesc &d = segs[s];
         KnnParams p;
         memset(&p, 0, sizeof p);
-        p.queries = nullptr; p.nq = 0; p.k = k; p.mode = mode == 1 ? KQ_MODE_NORMALS : KQ_MODE_KNN; p.rad = 1;
+        p.queries = nullptr; p.nq = 0; p.k = k; p.mode = mode == 1 ? KQ_MODE_NORMALS : KQ_MODE_KNN; p.rad = out->rad;
         p.r2cap = radius > 0 ? radius * radius : 0.0;
         p.mean = d.mean; p.cloud = d.cloud; p.normals = d.normals;
         p.qpts = d.pts0;
         // level 0: every point of the cloud, one thread each, against the level-0 grid
         KnnParams a = p;
         a.cap = out->cap_hist; a.gdev = d.g0; a.nq_dev = d.n; a.strag_flags = d.flags0;
+        a.vbi = d.vbi; a.rho_a = rho_a; a.rho_b = rho_b;
         h[s] = a;
         // level 1: the level-0 leftovers (list0), one warp each, against the coarse grid
         KnnParams b = p;
@@ -1525,37 +1668,70 @@ int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, 
     }
     KP_CUDA(ctx, cudaMalloc(&out->d_params, sizeof(KnnParams) * h.size()));
     KP_CUDA(ctx, cudaMemcpy(out->d_params, h.data(), sizeof(KnnParams) * h.size(), cudaMemcpyHostToDevice));
+    out->h_params = malloc(sizeof(KnnParams) * h.size());
+    memcpy(out->h_params, h.data(), sizeof(KnnParams) * h.size());
     // shared-memory opt-ins happen here, not inside a stream capture
     const size_t smem_w = (size_t)KQ_WARPS * capw * (sizeof(double) + sizeof(int));
     if (smem_w > 200 * 1024) return kp_set_err(ctx, KP_E_ARG, "k = %d neighbours is too many for the per-warp buffer", k);
     if (smem_w > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
     const size_t smem_h = (size_t)(k <= 32 ? 128 : 64) * ((size_t)out->cap_hist * 8 + (size_t)(k <= 32 ? 32 : 64) * 2);
     if (smem_h > 48 * 1024) {
-        if (k <= 32) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist_b<32, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
-        else KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist_b<64, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+        if (k <= 32) {
+            KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist_b<32, 2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+            KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist_b<32, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+            KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_vbi_b<32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+        } else {
+            KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist_b<64, 2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+            KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist_b<64, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+            KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_vbi_b<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+        }
     }
     return KP_OK;
 }
 void kp_knn_batch_destroy(KpKnnBatch *b)
 {
     if (b && b->d_params) { cudaFree(b->d_params); b->d_params = nullptr; }
+    if (b && b->h_params) { free(b->h_params); b->h_params = nullptr; }
+}
+template <int NB, int R, int T>
+static int knn_level0_launch(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows, int per_sm)
+{
+    const KnnParams *hp = (const KnnParams *)b.h_params;
+    const size_t smem = (size_t)T * ((size_t)b.cap_hist * 8 + NB * 2);
+    int64_t gx = (cap_rows + T - 1) / T;
+    if (gx > (int64_t)ctx->sm_count * per_sm) gx = (int64_t)ctx->sm_count * per_sm;
+    for (int s0 = 0; s0 < b.nseg; s0 += KNN_ARG_SEGS) {
+        const int ns = b.nseg - s0 < KNN_ARG_SEGS ? b.nseg - s0 : KNN_ARG_SEGS;
+        KnnBatchArgs a;
+        memset(&a, 0, sizeof a);
+        for (int i = 0; i < ns; ++i) a.p[i] = hp[s0 + i];
+        k_knn_hist_b<NB, R, T><<<dim3((unsigned)(gx > 0 ? gx : 1), (unsigned)ns), T, smem, ctx->stream>>>(a);
+        KP_LAUNCH_CHECK(ctx);
+    }
+    return KP_OK;
 }
 int kp_knn_batch_level0(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows)
 {
-    const KnnParams *pp = (const KnnParams *)b.d_params;
     KP_PROFB(ctx, "knn_level0", 0.0);
+    if (b.k <= 32) return b.rad == 2 ? knn_level0_launch<32, 2, 128>(ctx, b, cap_rows, 24) : knn_level0_launch<32, 1, 128>(ctx, b, cap_rows, 24);
+    return b.rad == 2 ? knn_level0_launch<64, 2, 64>(ctx, b, cap_rows, 32) : knn_level0_launch<64, 1, 64>(ctx, b, cap_rows, 32);
+}
+int kp_knn_batch_vbi(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows)
+{
+    const KnnParams *pp = (const KnnParams *)b.d_params;
+    KP_PROFB(ctx, "knn_vbi", 0.0);
     if (b.k <= 32) {
         constexpr int T = 128;
         const size_t smem = (size_t)T * ((size_t)b.cap_hist * 8 + 32 * 2);
         int64_t gx = (cap_rows + T - 1) / T;
         if (gx > (int64_t)ctx->sm_count * 24) gx = (int64_t)ctx->sm_count * 24;
-        k_knn_hist_b<32, 1, T><<<dim3((unsigned)(gx > 0 ? gx : 1), (unsigned)b.nseg), T, smem, ctx->stream>>>(pp);
+        k_knn_vbi_b<32, T><<<dim3((unsigned)(gx > 0 ? gx : 1), (unsigned)b.nseg), T, smem, ctx->stream>>>(pp);
     } else {
         constexpr int T = 64;
         const size_t smem = (size_t)T * ((size_t)b.cap_hist * 8 + 64 * 2);
         int64_t gx = (cap_rows + T - 1) / T;
         if (gx > (int64_t)ctx->sm_count * 32) gx = (int64_t)ctx->sm_count * 32;
-        k_knn_hist_b<64, 1, T><<<dim3((unsigned)(gx > 0 ? gx : 1), (unsigned)b.nseg), T, smem, ctx->stream>>>(pp);
+        k_knn_vbi_b<64, T><<<dim3((unsigned)(gx > 0 ? gx : 1), (unsigned)b.nseg), T, smem, ctx->stream>>>(pp);
     }
     KP_LAUNCH_CHECK(ctx);
     return KP_OK;

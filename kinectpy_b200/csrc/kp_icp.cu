@@ -70,6 +70,7 @@ struct IcpParams {
     double max_corr;
     double init_T[16];
     double *res_T, *res_fit, *res_rmse; int32_t *res_iters;   // where the converged state of the pair goes
+    const KpVbiDev *vbi;        // voxel-brick index over the target (device); used instead of the grid when it was built
 };
 
 __device__ __forceinline__ double icp_slack(const KpGridDev &g, double max_corr)
@@ -83,21 +84,15 @@ __device__ __forceinline__ double icp_slack(const KpGridDev &g, double max_corr)
     return eps * (2.0 * max_corr + eps) * 1.000001 + 4e-6 * (max_corr * max_corr);
 }
 
-// batched launches: parameter block of pair blockIdx.y from device memory into shared memory, with the device-side
-// grid layout, source count and slack patched in
-__device__ __forceinline__ const IcpParams &icp_params_batched(const IcpParams *pp)
+// batched launches: the parameter block of pair blockIdx.y straight from device memory (uniform, cached loads of the
+// fields a thread uses: no shared-memory copy, no barrier), with the device-side grid layout, source count and slack
+__device__ __forceinline__ IcpParams icp_params_batched(const IcpParams *__restrict__ pp)
 {
-    __shared__ IcpParams s_p;
-    const int *src = reinterpret_cast<const int *>(pp + blockIdx.y);
-    int *dst = reinterpret_cast<int *>(&s_p);
-    for (int i = threadIdx.x; i < (int)(sizeof(IcpParams) / 4); i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-    const int *gs = reinterpret_cast<const int *>(s_p.gdev);
-    int *gd = reinterpret_cast<int *>(&s_p.g);
-    for (int i = threadIdx.x; i < (int)(sizeof(KpGridDev) / 4); i += blockDim.x) gd[i] = gs[i];
-    if (threadIdx.x == 0) { s_p.ns = *s_p.ns_dev; s_p.slack = s_p.st->slack; }
-    __syncthreads();
-    return s_p;
+    IcpParams p = pp[blockIdx.y];
+    p.g = *p.gdev;
+    p.ns = *p.ns_dev;
+    p.slack = p.st->slack;
+    return p;
 }
 
 __global__ void __launch_bounds__(256) k_icp_init(const float *src, int ns, const __grid_constant__ IcpParams p, IcpState init,
@@ -111,47 +106,6 @@ __global__ void __launch_bounds__(256) k_icp_init(const float *src, int ns, cons
     out[3 * (int64_t)i] = kp_affine(T[0], T[1], T[2], T[3], X, Y, Z);
     out[3 * (int64_t)i + 1] = kp_affine(T[4], T[5], T[6], T[7], X, Y, Z);
     out[3 * (int64_t)i + 2] = kp_affine(T[8], T[9], T[10], T[11], X, Y, Z);
-}
-
-// 6x6 solve by Gaussian elimination with partial pivoting on the augmented matrix M[6][7] in shared memory,
-// executed by the whole (last) CTA: thread (r, j) = tid / 7, tid % 7 owns one element.  Every step performs
-// exactly the operations of the scalar loop nest (f = M[r][c] / M[c][c]; M[r][j] -= f * M[c][j] for j >= c),
-// element-parallel, so the result is the one a single thread would get, without its serial latency chain.
-// Returns (to every thread) whether the system was solvable; x[] is valid then.
-__device__ bool icp_solve6_cta(double (*M)[7], double *x, int tid)
-{
-    const int r = tid / 7, j = tid % 7;
-    const bool own = tid < 42;
-    bool ok = true;
-    for (int c = 0; c < 6; ++c) {
-        int pv = c;
-        double best = fabs(M[c][c]);
-        for (int rr = c + 1; rr < 6; ++rr) {
-            const double v = fabs(M[rr][c]);
-            if (v > best) { best = v; pv = rr; }
-        }
-        if (!(best > 1e-300)) { ok = false; break; }          // uniform: every thread read the same column
-        __syncthreads();
-        if (own && r == c && pv != c) { const double t = M[c][j]; M[c][j] = M[pv][j]; M[pv][j] = t; }
-        __syncthreads();
-        double nv = 0.0;
-        const bool upd = own && r > c && j >= c;
-        if (upd) { const double f = M[r][c] / M[c][c]; nv = M[r][j] - f * M[c][j]; }
-        __syncthreads();
-        if (upd) M[r][j] = nv;
-        __syncthreads();
-    }
-    if (ok && tid == 0) {
-        for (int rr = 5; rr >= 0; --rr) {
-            double sacc = M[rr][6];
-            for (int jj = rr + 1; jj < 6; ++jj) sacc -= M[rr][jj] * x[jj];
-            x[rr] = sacc / M[rr][rr];
-        }
-    }
-    __syncthreads();
-    if (ok)
-        for (int rr = 0; rr < 6; ++rr) if (!isfinite(x[rr])) ok = false;
-    return ok;
 }
 
 // nearest target point inside max_corr (position in g.pts, -1 = none); `prev` = last pass's partner or -1.
@@ -233,6 +187,82 @@ __device__ __forceinline__ int icp_nearest(const KpGridDev &g, double sx, double
         }
     }
     return bpos;
+}
+
+// The same search through the voxel-brick index of the (voxel-downsampled) target: the ball of radius
+// min(best so far, max_corr) around the source point is boxed in voxel coordinates, each brick the box touches
+// costs one 16-byte load and an AND of its occupancy word with the box mask, and only the voxels that survive are
+// looked at.  With the warm start the ball is a few millimetres wide: one or two bricks, one or two candidates.
+__device__ __forceinline__ int icp_nearest_vbi(const KpVbiDev &v, double sx, double sy, double sz, double r2, double slack, int prev)
+{
+    int bpos = -1, bi = -1;
+    double bd = INFINITY;
+    if (prev >= 0) {
+        const float4 q = __ldg(v.pts + prev);
+        const double d2 = kp_d2(sx, sy, sz, (double)q.x, (double)q.y, (double)q.z);
+        if (d2 < r2) { bd = d2; bi = __float_as_int(q.w); bpos = prev; }
+    }
+    const double lim0 = fmin(bd, r2);
+    // every point with d2 <= lim0 lies in a voxel whose box (widened by eps) meets the ball of this radius
+    const double rad = sqrt(lim0) * (1.0 + 1e-6) + v.eps + v.voxel * 1e-6;
+    KpVbiBox box;
+    if (!kp_vbi_box(v, sx, sy, sz, rad, box)) return bpos;
+    const float fx32 = (float)sx, fy32 = (float)sy, fz32 = (float)sz;
+    float lim32 = __double2float_ru(lim0 + slack);
+    kp_vbi_visit(v, box, [&](int pos, const float4 &q) {
+        const float ex = fx32 - q.x, ey = fy32 - q.y, ez = fz32 - q.z;
+        const float d32 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex));
+        if (d32 > lim32) return;
+        const double d2 = kp_d2(sx, sy, sz, (double)q.x, (double)q.y, (double)q.z);
+        const int id = __float_as_int(q.w);
+        if (d2 < r2 && (d2 < bd || (d2 == bd && id < bi))) {
+            bd = d2; bi = id; bpos = pos;
+            lim32 = __double2float_ru(bd + slack);
+        }
+    });
+    return bpos;
+}
+
+// last CTA, all threads: fitness / rmse / convergence test, 6x6 solve, next update
+// 6x6 solve by Gaussian elimination with partial pivoting on the augmented matrix M[6][7] in shared memory,
+// executed by the whole (last) CTA: thread (r, j) = tid / 7, tid % 7 owns one element.  Every step performs
+// exactly the operations of the scalar loop nest (f = M[r][c] / M[c][c]; M[r][j] -= f * M[c][j] for j >= c),
+// element-parallel, so the result is the one a single thread would get, without its serial latency chain.
+// Returns (to every thread) whether the system was solvable; x[] is valid then.
+__device__ bool icp_solve6_cta(double (*M)[7], double *x, int tid)
+{
+    const int r = tid / 7, j = tid % 7;
+    const bool own = tid < 42;
+    bool ok = true;
+    for (int c = 0; c < 6; ++c) {
+        int pv = c;
+        double best = fabs(M[c][c]);
+        for (int rr = c + 1; rr < 6; ++rr) {
+            const double v = fabs(M[rr][c]);
+            if (v > best) { best = v; pv = rr; }
+        }
+        if (!(best > 1e-300)) { ok = false; break; }          // uniform: every thread read the same column
+        __syncthreads();
+        if (own && r == c && pv != c) { const double t = M[c][j]; M[c][j] = M[pv][j]; M[pv][j] = t; }
+        __syncthreads();
+        double nv = 0.0;
+        const bool upd = own && r > c && j >= c;
+        if (upd) { const double f = M[r][c] / M[c][c]; nv = M[r][j] - f * M[c][j]; }
+        __syncthreads();
+        if (upd) M[r][j] = nv;
+        __syncthreads();
+    }
+    if (ok && tid == 0) {
+        for (int rr = 5; rr >= 0; --rr) {
+            double sacc = M[rr][6];
+            for (int jj = rr + 1; jj < 6; ++jj) sacc -= M[rr][jj] * x[jj];
+            x[rr] = sacc / M[rr][rr];
+        }
+    }
+    __syncthreads();
+    if (ok)
+        for (int rr = 0; rr < 6; ++rr) if (!isfinite(x[rr])) ok = false;
+    return ok;
 }
 
 // last CTA, all threads: fitness / rmse / convergence test, 6x6 solve, next update
@@ -334,11 +364,14 @@ __device__ __forceinline__ void icp_iter_body(const IcpParams &p)
             p.cur[3 * (int64_t)i] = sx; p.cur[3 * (int64_t)i + 1] = sy; p.cur[3 * (int64_t)i + 2] = sz;
         }
         int bpos = -1;
-        if (!isnan(sx) && g.dim[0] > 0) bpos = icp_nearest(g, sx, sy, sz, p.r2, p.slack, prev);
+        const bool use_vbi = p.vbi != nullptr && p.vbi->ok;
+        if (use_vbi) {
+            if (!isnan(sx)) { const KpVbiDev v = *p.vbi; bpos = icp_nearest_vbi(v, sx, sy, sz, p.r2, p.slack, prev); }
+        } else if (!isnan(sx) && g.dim[0] > 0) bpos = icp_nearest(g, sx, sy, sz, p.r2, p.slack, prev);
         p.corr[i] = bpos;
         if (bpos >= 0) {
             has = true;
-            const float4 q = __ldg(g.pts + bpos);
+            const float4 q = __ldg((use_vbi ? p.vbi->pts : g.pts) + bpos);
             const int bi = __float_as_int(q.w);
             const double ex = sx - (double)q.x, ey = sy - (double)q.y, ez = sz - (double)q.z;
             bd = (ex * ex + ey * ey) + ez * ez;
@@ -473,13 +506,14 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __
     icp_iter_body<MODE>(p);
 }
 template <int MODE>
-__global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter_b(const IcpParams *pp)
+__global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_iter_b(const IcpParams *pp)
 {
     // CTAs beyond the pair's source count, and every CTA of a converged pair, leave before touching anything else
     const IcpParams *me = pp + blockIdx.y;
     const int ns = *me->ns_dev;
     if (blockIdx.x * ICP_THREADS >= (unsigned)max(ns, 1) || me->st->done) return;
-    icp_iter_body<MODE>(icp_params_batched(pp));
+    const IcpParams p = icp_params_batched(pp);      // thread-local copy: the loops read registers, not shared memory
+    icp_iter_body<MODE>(p);
 }
 // batched init: moving source = init * src, state reset, slack from the device-side grid
 __global__ void __launch_bounds__(256) k_icp_init_b(const IcpParams *pp)
@@ -490,7 +524,15 @@ __global__ void __launch_bounds__(256) k_icp_init_b(const IcpParams *pp)
         IcpState init;
         memset(&init, 0, sizeof init);
         for (int i = 0; i < 16; ++i) { init.T[i] = p->init_T[i]; init.U[i] = (i % 5 == 0) ? 1.0 : 0.0; }
-        init.slack = icp_slack(*p->gdev, p->max_corr);
+        if (p->vbi && p->vbi->ok) {
+            // the same bound from the index's extent (the grid is empty when the index took the cloud)
+            const KpVbiDev &v = *p->vbi;
+            double M = 0.0;
+            for (int c = 0; c < 3; ++c)
+                M = fmax(M, fmax(fabs(v.minb[c]), fabs(v.minb[c] + v.voxel * (double)v.nvox[c])) + 2.0 * p->max_corr);
+            const double eps = 8.0 * M / 16777216.0;
+            init.slack = eps * (2.0 * p->max_corr + eps) * 1.000001 + 4e-6 * (p->max_corr * p->max_corr);
+        } else init.slack = icp_slack(*p->gdev, p->max_corr);
         *p->st = init;
     }
     const double *T = p->init_T;
@@ -541,7 +583,7 @@ int kp_icp_batch_create(kp_ctx *ctx, const KpIcpPairDesc *pairs, int npairs, int
         p.st = (IcpState *)take(sizeof(IcpState));
         p.r2 = max_corr * max_corr; p.max_corr = max_corr;
         p.max_iter = out->max_iter; p.rel_fit = rel_fitness; p.rel_rmse = rel_rmse;
-        p.gdev = pairs[i].tgt_grid; p.ns_dev = pairs[i].n_src; p.src = pairs[i].src;
+        p.gdev = pairs[i].tgt_grid; p.ns_dev = pairs[i].n_src; p.src = pairs[i].src; p.vbi = pairs[i].tgt_vbi;
         for (int e = 0; e < 16; ++e) p.init_T[e] = pairs[i].init_T[e];
         p.res_T = pairs[i].res_T; p.res_fit = pairs[i].res_fit; p.res_rmse = pairs[i].res_rmse; p.res_iters = pairs[i].res_iters;
         h[i] = p;

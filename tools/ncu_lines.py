@@ -1,26 +1,32 @@
-"""Aggregate an `ncu --page source --csv --print-source cuda,sass` export per CUDA source line.
-usage: python tools_ncu_lines.py <report.ncu-rep> <kernel-name> [launch-skip] [top]"""
-import csv, subprocess, sys, collections
-rep, kern = sys.argv[1], sys.argv[2]
-skip = sys.argv[3] if len(sys.argv) > 3 else "0"
-top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", kern,
-                      "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-agg = collections.OrderedDict()
-fname = None; hdr = None; cur = None
+#!/usr/bin/env python
+"""Per-CUDA-source-line totals (instructions executed, stall samples) from `ncu --page source --print-source cuda,sass --csv`."""
+import csv, sys
+rows = list(csv.reader(open(sys.argv[1])))
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+cur_file = None
+hdr = None
+agg = []
 for r in rows:
-    if not r: continue
-    if r[0] == "File Path": fname = r[1].split("/")[-1]; continue
-    if r[0] == "Function Name": continue
-    if r[0] == "Line No": hdr = r; si = r.index("# Samples"); ii = r.index("Instructions Executed"); ti = r.index("Thread Instructions Executed"); continue
-    if hdr is None or len(r) <= ii: continue
-    if r[0] != "": cur = (fname, r[0], r[1].strip()[:100])
-    if r[2] == "": continue     # source-only row
-    a = agg.setdefault(cur, [0, 0, 0])
-    num = lambda x: int(x) if x.strip().lstrip('-').isdigit() else 0
-    a[0] += num(r[si]); a[1] += num(r[ii]); a[2] += num(r[ti])
-ts = sum(a[0] for a in agg.values()) or 1; tn = sum(a[1] for a in agg.values()) or 1
-print("samples", ts, "warp-inst", tn)
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-    print("%5.1f%% smp %5.1f%% inst act %4.1f | %s:%s | %s" % (100 * a[0] / ts, 100 * a[1] / tn, a[2] / max(a[1], 1), k[0], k[1], k[2]))
+    if len(r) == 2 and r[0] == "File Path":
+        cur_file = r[1].split("/")[-1]
+        continue
+    if r and r[0] == "Line No":
+        hdr = r
+        i_inst = hdr.index("Instructions Executed")
+        i_samp = hdr.index("# Samples")
+        i_thr = hdr.index("Thread Instructions Executed")
+        continue
+    if hdr and r and r[0] not in ("", "Function Name") and r[2] == "-":
+        try:
+            agg.append((int(r[i_inst]), int(r[i_samp]), int(r[i_thr]), cur_file, r[0], r[1][:110]))
+        except (ValueError, IndexError):
+            pass
+tot_i = sum(a[0] for a in agg) or 1
+tot_s = sum(a[1] for a in agg) or 1
+print("total warp instructions %d, samples %d" % (tot_i, tot_s))
+print("--- by instructions")
+for a in sorted(agg, reverse=True)[:top]:
+    print("%5.1f%% inst %5.1f%% samp  lanes %4.1f  %s:%s  %s" % (100.0 * a[0] / tot_i, 100.0 * a[1] / tot_s, a[2] / max(a[0], 1), a[3], a[4], a[5]))
+print("--- by stall samples")
+for a in sorted(agg, key=lambda x: -x[1])[:top]:
+    print("%5.1f%% inst %5.1f%% samp  lanes %4.1f  %s:%s  %s" % (100.0 * a[0] / tot_i, 100.0 * a[1] / tot_s, a[2] / max(a[0], 1), a[3], a[4], a[5]))
