@@ -5,14 +5,16 @@ Workload (BASELINE.json configs[3], "C4"): a synthetic 3-sensor WFOV 1024x1024 d
 per frame unproject -> transform -> fuse -> 1 cm voxel -> SOR(20, 2.0) -> floor removal
 (20 cm band, RANSAC 1 cm / 1000 hypotheses, merge, SOR(50, 0.30)) -> point-to-plane ICP refinement
 of both sub extrinsics (1 cm voxel, normals r = 2 cm / 30 nn, max_corr 2 cm, <= 30 iterations).
-A "step" is one batch of --frames-per-step frames per rank; frames are sharded over ranks with no
-collective on the frame path (weak scaling: per-GPU work is fixed).
+A "step" is one call of the frame engine over --frames-per-step frames per rank; frames are sharded over
+ranks with no collective on the frame path (weak scaling: per-GPU work is fixed).  The engine is driven by
+ONE host thread per GPU: B frames per kernel launch, W batch slots in flight, one CUDA graph per slot.
 
   python bench.py --gpus 1 --steps K --warmup W            # our arm
   python bench.py --impl reference ...                     # CPU arm: the oracle port on the host cores
   torchrun ... bench.py --gpus N ...                       # one rank per GPU
 
-Prints ONE JSON line on rank 0.
+Prints ONE JSON line on rank 0.  Beside the headline (C4) it carries driver-run legs for the other BASELINE
+configs: C1 (1 x NFOV: voxel + SOR), C2 (3 x NFOV: ICP ms/pair), C3 (RANSAC on the fused WFOV cloud), C5 (resample).
 """
 from __future__ import annotations
 
@@ -33,6 +35,8 @@ if ROOT not in sys.path:
 
 METRIC = "fused_3kinect_frames_per_s"
 UNIT = "frames/s"
+ICP_START = {"angle_deg": 0.3, "shift_mm": [3, -3, 3]}     # ground truth perturbed by this much
+SENSOR_YAW_DEG = [0.0, 40.0, -40.0]
 
 
 def parse():
@@ -42,15 +46,14 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="WFOV", choices=["WFOV", "NFOV"])
-    ap.add_argument("--frames-per-step", type=int, default=0, help="frames per step and GPU (0 = 2 x streams)")
+    ap.add_argument("--frames-per-step", type=int, default=0, help="frames per step and GPU (0 = 2 x frames in flight)")
     ap.add_argument("--distinct-frames", type=int, default=4, help="synthetic frames rendered per rank (cycled)")
-    ap.add_argument("--streams", type=int, default=0,
-                    help="frames in flight per GPU (0 = auto: 6 while every worker thread has a core to spin on, "
-                         "8 with sleeping waits when the box's ranks outnumber its cores)")
+    ap.add_argument("--streams", type=int, default=16, help="frames in flight per GPU (B frames per launch x W batch slots)")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-resample", action="store_true", help="skip the config-C5 resampling leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the C1 / C2 / C3 legs")
     return ap.parse_args()
 
 
@@ -66,60 +69,74 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of THIS rank's GPU, sampled every 200 ms during the timed region through NVML
+    inside the process (a thread that sleeps between two cheap queries).  Round 1 started one `nvidia-smi -lms`
+    process per rank: eight of them disturbed the 8-GPU run they were meant to watch."""
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop_flag = threading.Event()
+        self.th = None
+        self.err = None
+
+    def _loop(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.idx
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.idx])
+                except Exception:
+                    pass
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            while not self.stop_flag.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(mx))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for name, b in bits.items():
+                        if r & b:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                self.stop_flag.wait(0.2)
+        except Exception as e:       # no NVML: one nvidia-smi query instead of a loop
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+        self.stop_flag.set()
+        if self.th:
+            self.th.join(timeout=2)
+        if not self.sm:
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 1, "source": "nvidia-smi after the region (NVML unavailable: %s)" % self.err}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "NVML, this rank's GPU, 200 ms period"}
 
 
-def make_inputs(mode_name, distinct, rank, scale=1e-3):
+def make_inputs(mode_name, distinct, rank, scale=1e-3, sensors=3):
     from kinectpy_b200 import synth
     mode = synth.MODES[mode_name]
-    depth, tab, T = synth.render_sequence(mode, distinct, 3, first_frame=rank * distinct)
+    depth, tab, T = synth.render_sequence(mode, distinct, sensors, first_frame=rank * distinct)
     T_fuse = synth.scale_extrinsics(T, scale)
-    T_icp = np.stack([synth.perturbed_extrinsic(T_fuse[s], 0.3, (3, -3, 3), unit_scale=scale) if s else T_fuse[s]
-                      for s in range(3)])
+    T_icp = np.stack([synth.perturbed_extrinsic(T_fuse[s], ICP_START["angle_deg"], tuple(ICP_START["shift_mm"]), unit_scale=scale) if s else T_fuse[s]
+                      for s in range(sensors)])
     return mode, depth, tab, T_fuse, T_icp
 
 
@@ -139,31 +156,82 @@ def cpu_baseline(cfg, depth, tab, T_fuse, T_icp, frames):
             "seconds": round(dt, 3), "stage_seconds": {k: round(v, 3) for k, v in tm.items()}}
 
 
+# kernel family of the profile -> (dominant kernel, binding resource)
+LEAF = {
+    "knn_level0": ("k_knn_hist_b", "issue"), "knn_level1": ("k_knn_wbf_b", "issue"), "knn_stragglers": ("k_knn_b", "issue"),
+    "knn_vbi": ("k_knn_vbi_b", "issue"), "icp": ("k_icp_iter_b", "issue"),
+    "radix_sort": ("k_rs_scatter", "hbm"), "ransac_score": ("k_e_ransac_score", "fp64"), "ransac_fit": ("k_e_ransac_fit", "latency"),
+    "ransac_select": ("k_e_ransac_select", "latency"),
+    "unproject_transform": ("k_unproject", "hbm"), "voxel_mean": ("k_e_voxel_mean", "hbm"), "voxel_keys": ("k_e_voxel_keys", "hbm"),
+    "grid_build": ("k_eg_scatter", "hbm"), "vbi_build": ("k_vbi_scatter", "hbm"), "compact_rows": ("k_bc_scatter", "hbm"),
+    "compact_index": ("k_bc_scatter", "hbm"), "run_heads": ("k_bc_scatter", "hbm"), "sor_stats": ("k_bcsum_level", "hbm"),
+    "band_mask": ("k_e_band_mask", "hbm"), "merge": ("k_e_append_rows", "hbm"),
+}
+
+
+def family_bytes(st, cfg, S, P):
+    """Algorithmic HBM bytes per FRAME of every streaming family, from the frame's own counts.
+    N = fused rows, Nv = valid, M = voxels, K = kept by SOR, lo = band, E = merged, per ICP cloud P rows."""
+    NP = S * P
+    Nv, M, K, E = st["n_fused"], st["n_voxel"], st["n_sor"], st["n_merged"]
+    lo = st["n_lo"]
+    icp = 1 if (cfg.do_icp and S > 1) else 0
+    Mi = st["n_icp"]                                         # voxel counts of the S ICP clouds
+    b = {}
+    b["unproject_transform"] = NP * (2 + 12 + 12 * icp) + NP * 8
+    b["voxel_keys"] = (NP + icp * NP) * (12 + 4)
+    b["radix_sort"] = (NP + icp * NP) * (4 * 2 * 8 + 4)      # 4 passes x (key + index) read and written, one histogram read each
+    b["run_heads"] = (Nv + icp * sum(st["nv_icp"])) * 2 * 4
+    b["voxel_mean"] = (Nv + icp * sum(st["nv_icp"])) * (4 + 12) + (M + icp * sum(Mi)) * (12 + 4)
+    # neighbour grids: level 0 + level 1 of SOR and floor SOR, level 0 + 1 of the ICP target: 12 B read per pass (4 passes) + rank / loc + 16 B row
+    gpts = 2 * M + 2 * E + icp * 2 * Mi[0]
+    b["grid_build"] = gpts * (3 * 12 + 4 * 4 + 16)
+    b["sor_stats"] = (M + E) * (3 * 8 + 1)
+    b["compact_rows"] = (M + K + lo + E) * (2 * 1 + 12) + (K + K + (lo - st["n_inl"]) + st["n_out"]) * 12
+    b["compact_index"] = 2 * (2 * M + 2 * E + icp * 2 * Mi[0]) * 1
+    b["band_mask"] = K * (2 * 12 + 1)
+    b["merge"] = (K - lo) * 24
+    b["ransac_score"] = lo * 12 + cfg.ransac_iters * 40
+    b["knn_level0"] = (M + E + icp * Mi[0]) * 16 + (M + E) * 8 + icp * Mi[0] * 12
+    b["icp"] = 0.0
+    return b
+
+
+def run_pipeline_leg(ctx, cfg, depth, tab, T_fuse, T_icp, device, frames, steps):
+    """frames/s of a pipeline configuration with depth resident in HBM (CUDA events on the ctx stream, L2 flushed)."""
+    from kinectpy_b200.pipeline import FramePipeline
+    pipe = FramePipeline(cfg, tab, T_fuse, T_icp, device=device)
+    batch = np.ascontiguousarray(depth[np.arange(frames) % depth.shape[0]])
+    d = pipe.upload(batch)
+    for _ in range(3):
+        res = pipe.run_raw(d.ptr, True, frames)
+    ms = 0.0
+    for _ in range(steps):
+        ctx.flush_l2(); ctx.sync(); ctx.timer_start()
+        res = pipe.run_raw(d.ptr, True, frames)
+        ms += ctx.timer_stop()
+    return pipe, d, res, ms / steps
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # Host side of the frame pipeline: one worker thread per frame in flight.  A worker waits for its stream ~12
-    # times per frame; spinning waits are fastest while the box has cores to spare, sleeping waits (measured: 8 frames
-    # in flight sleeping reach 97 % of 6 spinning) when the workers of all ranks together would crowd the cores.
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(max(world, 1))))
-    if "KP_SYNC" not in os.environ:
-        # measured: 14 spinning workers on 24 cores scale 2.01 x over one GPU, 28 on 32 cores only 3.60 x over four:
-        # spin only while the box's workers stay under ~60 % of its cores
-        os.environ["KP_SYNC"] = "block" if local_world * 7 * 10 > cores * 6 else "spin"
-    if args.streams <= 0:
-        args.streams = 8 if os.environ["KP_SYNC"] == "block" else 6
-    if args.frames_per_step <= 0:
-        args.frames_per_step = 2 * args.streams
     from kinectpy_b200.pipeline import PipelineConfig
     mode_px = {"WFOV": 1024 * 1024, "NFOV": 640 * 576}[args.mode]
     cfg = PipelineConfig(n_sensors=3, pixels=mode_px, n_streams=args.streams)
+    if args.frames_per_step <= 0:
+        args.frames_per_step = 2 * args.streams
     workload = ("C4: 3 x %s synthetic depth frames -> unproject+transform+fuse -> voxel 1cm -> SOR(20,2.0) -> "
                 "floor removal (band 20cm, RANSAC 1cm x1000, SOR(50,0.30)) -> p2plane ICP x2 (max_corr 2cm, <=30 it)" % args.mode)
     config = {"workload": workload, "mode": args.mode, "sensors": 3, "frames_per_step_per_gpu": args.frames_per_step,
-              "distinct_frames": args.distinct_frames, "streams_per_gpu": args.streams, "host_wait": os.environ["KP_SYNC"], "host_cores": cores, "sharding": "frames round-robin over ranks, no collective",
+              "distinct_frames": args.distinct_frames, "frames_in_flight_per_gpu": args.streams, "host_threads_per_gpu": 1,
+              "host_cores": cores, "sharding": "frames round-robin over ranks, no collective",
+              "icp_start": "ground-truth extrinsic perturbed by %.1f deg about (1,1,1)/sqrt(3) and (%+d,%+d,%+d) mm" %
+                           (ICP_START["angle_deg"], *ICP_START["shift_mm"]),
+              "sensor_yaw_deg": SENSOR_YAW_DEG,
               "l2": "flushed between timed steps (256 MiB memset on the timing stream)",
               "arithmetic": "decisions and sums in f64 on f32-stored points (no FMA contraction); fp32 only pre-selects candidates"}
 
@@ -208,6 +276,9 @@ def main():
     mode, depth, tab, T_fuse, T_icp = make_inputs(args.mode, args.distinct_frames, rank)
     S, P, B = 3, mode.pixels, args.frames_per_step
     pipe = FramePipeline(cfg, tab, T_fuse, T_icp, device=local_rank)
+    fpl, slots = pipe.frames_in_flight()
+    config["frames_per_launch"] = fpl
+    config["batch_slots"] = slots
     ctx = _cabi.default_context(local_rank)
     batch = np.ascontiguousarray(depth[np.arange(B) % depth.shape[0]])      # uint16 [B,S,P]
     d_batch = pipe.upload(batch)
@@ -218,12 +289,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, profile):
-        """K steps, each bracketed by CUDA events on the ctx stream (the step call returns only after its
-        worker streams are drained, so the event pair spans the whole step); L2 flushed between steps."""
+    def timed(fn, steps):
+        """K steps, each bracketed by CUDA events on the ctx stream (a step call returns only after every batch
+        slot's streams are drained, so the event pair spans the whole step); L2 flushed between steps."""
         total_ms = 0.0
-        if profile:
-            pipe.profile(True)
         for _ in range(steps):
             ctx.flush_l2()
             ctx.sync()
@@ -240,32 +309,11 @@ def main():
     sampler.start()
     l0 = pipe.launch_count()
     wall0 = time.perf_counter()
-    ms = timed(step_dev, args.steps, profile=False)     # the headline number carries no profiling events
+    ms = timed(step_dev, args.steps)                    # the headline number carries no profiling events
     barrier()
     wall = time.perf_counter() - wall0
     launches = pipe.launch_count() - l0
     clocks = sampler.stop()
-
-    # Per-kernel durations: with several frames in flight an event pair on one stream also spans the
-    # time its kernels wait behind the other streams' work, so the same steps are re-run with ONE frame
-    # in flight and profiled there (CUDA events on the launching stream, L2 flushed between steps).
-    if True:   # (also with --streams 1: the headline run carries no profiling events)
-        import copy as _copy
-        cfg1 = _copy.copy(cfg)
-        cfg1.n_streams = 1
-        pipe1 = FramePipeline(cfg1, tab, T_fuse, T_icp, device=local_rank)
-        pipe1.run_raw(d_batch.ptr, True, min(B, 2))
-        psteps = max(1, min(args.steps, 3))
-        pipe1.profile(True)
-        ms_serial = 0.0
-        for _ in range(psteps):
-            ctx.flush_l2(); ctx.sync(); ctx.timer_start()
-            pipe1.run_raw(d_batch.ptr, True, B)
-            ms_serial += ctx.timer_stop()
-        prof = pipe1.profile_read()
-        pipe1.profile(False)
-        pipe1.close()
-        prof_frames = B * psteps
 
     # ------------------------------------------------------------------ e2e: host buffers in, clouds out
     e2e = None
@@ -280,71 +328,14 @@ def main():
         for _ in range(2):
             res = step_e2e()
         barrier()
-        ms_e2e = timed(step_e2e, args.steps, profile=False)
+        ms_e2e = timed(step_e2e, args.steps)
         barrier()
         d2h = sum(int(res[f].n_out) * 12 for f in range(B)) + B * C.sizeof(_cabi.FrameResult)
         e2e = {"ms": ms_e2e, "h2d": int(batch.nbytes), "d2h": int(d2h)}
         lib.kp_host_free(hin)
         lib.kp_host_free(hout)
 
-    # ------------------------------------------------------------------ config C5: crop'd clouds -> [B, 4096, 3]
-    c5 = None
-    if not args.no_resample and rank == 0:
-        # the final clouds of one step (device resident) resampled to PointNet's input, N = 4096 per frame
-        n_out = [int(last[f].n_out) for f in range(B)]
-        stride = S * P
-        d_out = ctx.empty((B, stride, 3), np.float32)
-        pipe.run_raw(d_batch.ptr, True, B, d_out_ptr=d_out.ptr, out_stride=stride)
-        off = np.zeros(B + 1, np.int64)
-        # frames sit at stride intervals: compact the offsets into one CSR over a packed copy
-        packed = ctx.empty((sum(n_out), 3), np.float32)
-        pos = 0
-        for f in range(B):
-            ctx.check(ctx.lib.kp_memcpy_d2d(ctx.handle, packed.ptr + 12 * pos, d_out.ptr + 12 * f * stride, 12 * n_out[f]))
-            pos += n_out[f]
-            off[f + 1] = pos
-        out_t = ctx.empty((B, 4096, 3), np.float32)
-        fn = lambda: ctx.check(ctx.lib.kp_resample_batch(ctx.handle, packed.ptr, off.ctypes.data_as(C.POINTER(C.c_int64)), B, 4096, 0,
-                                                         1234, 0, out_t.ptr, None))
-        for _ in range(3):
-            fn()
-        ctx.sync()
-        ms_c5 = 0.0
-        reps = 5
-        for _ in range(reps):
-            ctx.flush_l2(); ctx.sync(); ctx.timer_start(); fn(); ms_c5 += ctx.timer_stop()
-        c5 = {"clouds_per_s": B * reps / (ms_c5 * 1e-3), "ms_per_cloud": ms_c5 / (B * reps), "points_in": int(np.mean(n_out)),
-              "points_out": 4096, "algorithmic_GBps": round((sum(n_out) * (12 + 4 + 3 * 4) + B * 4096 * 32) * reps / (ms_c5 * 1e-3) / 1e9, 1),
-              "algorithmic_bytes": "per point 12 (row read for the key) + 4 (key write) + 3 x 4 (radix-select passes); per output 32"}
-        del d_out, packed, out_t
-
-    # ------------------------------------------------------------------ K1 batched: the step's B frames in ONE launch
-    k1b = None
-    if rank == 0:
-        # kp_unproject_transform over [B][S][P] depth: the table tile stays in registers for all B frames, so the launch
-        # moves B*S*P*(2 + 12) + S*P*8 bytes.  Same events / L2 flush as everything else.
-        d_tab1 = ctx.to_device(np.ascontiguousarray(tab, np.float32), np.float32)
-        xyz1 = ctx.empty((B, S * P, 3), np.float32)
-        bnd1 = ctx.empty((B, 6), np.float32)
-        nv1 = ctx.empty((B,), np.int32)
-        Tf = np.ascontiguousarray(T_fuse, np.float64).reshape(-1)
-        fn1 = lambda: ctx.check(ctx.lib.kp_unproject_transform(ctx.handle, d_batch.ptr, d_tab1.ptr, Tf.ctypes.data, B, S, P,
-                                                               cfg.unproject_flags, float(cfg.scale), xyz1.ptr, None, None,
-                                                               bnd1.ptr, nv1.ptr))
-        for _ in range(3):
-            fn1()
-        ctx.sync()
-        ms_k1, reps = 0.0, 5
-        for _ in range(reps):
-            ctx.flush_l2(); ctx.sync(); ctx.timer_start(); fn1(); ms_k1 += ctx.timer_stop()
-        by1 = B * S * P * 14.0 + S * P * 8.0
-        pk1, _ = peaks()
-        k1b = {"frames_per_launch": B, "ms_per_launch": round(ms_k1 / reps, 4), "algorithmic_GBps": round(by1 * reps / (ms_k1 * 1e-3) / 1e9, 1),
-               "frac_of_hbm_peak": round(by1 * reps / (ms_k1 * 1e-3) / 1e9 / pk1, 4),
-               "note": "unproject + extrinsic + fuse + per-frame bounds, 3 launches (K1, bounds fold, decode) inside the timed region"}
-        del d_tab1, xyz1, bnd1, nv1
-
-    # ------------------------------------------------------------------ reduce over ranks (max time)
+    # ------------------------------------------------------------------ reduce over ranks (max time) before the rank-0-only legs
     if world > 1:
         t = torch.tensor([ms, e2e["ms"] if e2e else 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -354,50 +345,149 @@ def main():
     frames_total = world * B * args.steps
     value = frames_total / (ms * 1e-3)
 
+    prof, prof_frames, ms_serial, c5, legs, stats = {}, 1, 0.0, None, {}, None
+    if rank == 0:
+        # Per-kernel durations: the same frames through ONE frame per launch, one batch at a time, as direct launches
+        # with a CUDA event pair around every kernel family (profiling mode of the engine), L2 flushed between steps.
+        import copy as _copy
+        cfg1 = _copy.copy(cfg)
+        cfg1.n_streams = fpl                 # the same frames per launch as the timed region, ONE batch in flight
+        pipe1 = FramePipeline(cfg1, tab, T_fuse, T_icp, device=local_rank)
+        pipe1.run_raw(d_batch.ptr, True, fpl)
+        psteps = max(1, min(args.steps, 3))
+        nprof = max(fpl, (min(B, 8) // fpl) * fpl)
+        pipe1.profile(True)
+        for _ in range(psteps):
+            ctx.flush_l2(); ctx.sync(); ctx.timer_start()
+            pipe1.run_raw(d_batch.ptr, True, nprof)
+            ms_serial += ctx.timer_stop()
+        prof = pipe1.profile_read()
+        pipe1.profile(False)
+        stats = pipe1.frame_counts()
+        pipe1.close()
+        prof_frames = nprof * psteps
+
+        # ---------------------------------------------------------------- config C5: final clouds -> [B, 4096, 3]
+        if not args.no_resample:
+            n_out = [int(last[f].n_out) for f in range(B)]
+            stride = S * P
+            d_out = ctx.empty((B, stride, 3), np.float32)
+            pipe.run_raw(d_batch.ptr, True, B, d_out_ptr=d_out.ptr, out_stride=stride)
+            off = np.zeros(B + 1, np.int64)
+            packed = ctx.empty((sum(n_out), 3), np.float32)
+            pos = 0
+            for f in range(B):
+                ctx.check(ctx.lib.kp_memcpy_d2d(ctx.handle, packed.ptr + 12 * pos, d_out.ptr + 12 * f * stride, 12 * n_out[f]))
+                pos += n_out[f]
+                off[f + 1] = pos
+            out_t = ctx.empty((B, 4096, 3), np.float32)
+            fn = lambda: ctx.check(ctx.lib.kp_resample_batch(ctx.handle, packed.ptr, off.ctypes.data_as(C.POINTER(C.c_int64)), B, 4096, 0,
+                                                             1234, 0, out_t.ptr, None))
+            for _ in range(3):
+                fn()
+            ctx.sync()
+            ms_c5 = 0.0
+            reps = 5
+            for _ in range(reps):
+                ctx.flush_l2(); ctx.sync(); ctx.timer_start(); fn(); ms_c5 += ctx.timer_stop()
+            c5 = {"clouds_per_s": B * reps / (ms_c5 * 1e-3), "ms_per_cloud": ms_c5 / (B * reps), "points_in": int(np.mean(n_out)),
+                  "points_out": 4096, "algorithmic_GBps": round((sum(n_out) * (12 + 4 + 3 * 4) + B * 4096 * 32) * reps / (ms_c5 * 1e-3) / 1e9, 1),
+                  "algorithmic_bytes": "per point 12 (row read for the key) + 4 (key write) + 3 x 4 (radix-select passes); per output 32"}
+            del d_out, packed, out_t
+
+        # ---------------------------------------------------------------- legs for BASELINE configs C1, C2, C3
+        if not args.no_legs:
+            from kinectpy_b200 import synth
+            # C1: ONE NFOV sensor -> 1 cm voxel -> SOR(20, 2.0)
+            _, d1, t1, Tf1, Ti1 = make_inputs("NFOV", 2, 0, sensors=1)
+            cfgc1 = PipelineConfig(n_sensors=1, pixels=synth.NFOV.pixels, do_floor=False, do_icp=False, n_streams=16)
+            p1, dd1, r1, ms1 = run_pipeline_leg(ctx, cfgc1, d1, t1, Tf1, Ti1, local_rank, 32, 3)
+            legs["C1_nfov_voxel_sor"] = {"frames_per_s": round(32 / (ms1 * 1e-3), 1), "ms_per_frame": round(ms1 / 32, 4),
+                                         "points": int(r1[0].n_fused), "voxels": int(r1[0].n_voxel), "kept": int(r1[0].n_sor),
+                                         "workload": "1 x NFOV 640x576 -> unproject -> voxel 1 cm -> SOR(20, 2.0), 32 frames per step, depth resident"}
+            p1.close(); del dd1
+            # C2: 3 x NFOV fused + point-to-plane ICP of both subs (max_corr 2 cm, <= 30 iterations): ms / pair from the profile
+            _, d2, t2, Tf2, Ti2 = make_inputs("NFOV", 2, 0)
+            cfgc2 = PipelineConfig(n_sensors=3, pixels=synth.NFOV.pixels, n_streams=1)
+            p2 = FramePipeline(cfgc2, t2, Tf2, Ti2, device=local_rank)
+            dd2 = p2.upload(d2)
+            p2.run_raw(dd2.ptr, True, 2)
+            p2.profile(True)
+            ctx.flush_l2(); ctx.sync()
+            r2 = p2.run_raw(dd2.ptr, True, 2)
+            pr2 = p2.profile_read()
+            p2.profile(False)
+            npairs = 2 * 2
+            legs["C2_nfov_icp"] = {"icp_ms_per_pair": round(pr2["icp"]["ms"] / npairs, 4), "pairs": npairs,
+                                   "iters": [int(r2[0].icp_iters[i]) for i in range(2)], "fitness": [round(float(r2[0].icp_fitness[i]), 4) for i in range(2)],
+                                   "source_points": int(p2.frame_counts()["n_icp"][1]), "target_points": int(p2.frame_counts()["n_icp"][0]),
+                                   "workload": "3 x NFOV fused; sub_i -> master on 1 cm voxel clouds, normals r = 2 cm / 30 nn, max_corr 2 cm, <= 30 it, 1e-6 / 1e-6; "
+                                               "one frame (two pairs) per launch, one batch in flight: the latency of a pair, not its share of a full GPU"}
+            p2.close(); del dd2
+            # C3: segment_plane(1 cm, n = 3, 1000 hypotheses) on the whole fused WFOV cloud through the C ABI
+            xyz = ctx.empty((S * P, 3), np.float32)
+            dtab = ctx.to_device(np.ascontiguousarray(tab, np.float32), np.float32)
+            Tf = np.ascontiguousarray(T_fuse, np.float64).reshape(-1)
+            ctx.check(ctx.lib.kp_unproject_transform(ctx.handle, d_batch.ptr, dtab.ptr, Tf.ctypes.data, 1, S, P, cfg.unproject_flags,
+                                                     float(cfg.scale), xyz.ptr, None, None, None, None))
+            comp = ctx.empty((S * P, 3), np.float32)
+            nfused = C.c_int64()
+            ctx.check(ctx.lib.kp_compact(ctx.handle, S * P, None, 0, xyz.ptr, comp.ptr, None, None, None, None, None, C.byref(nfused)))
+            plane = (C.c_double * 4)()
+            ninl, best = C.c_int64(), C.c_int32()
+            fn3 = lambda: ctx.check(ctx.lib.kp_ransac_plane(ctx.handle, comp.ptr, nfused.value, 0.01, 3, 1000, 0.99999999, 1234, plane, None,
+                                                            C.byref(ninl), C.byref(best), None))
+            for _ in range(2):
+                fn3()
+            ms3, reps = 0.0, 5
+            for _ in range(reps):
+                ctx.flush_l2(); ctx.sync(); ctx.timer_start(); fn3(); ms3 += ctx.timer_stop()
+            ms3 /= reps
+            props = torch.cuda.get_device_properties(local_rank)
+            fp64_peak = props.multi_processor_count * 64 * 2 * 1.965e9 / 1e12      # 64 FP64 FMA lanes per SM and clock
+            flops = 7.0 * nfused.value * 1000
+            legs["C3_ransac_fused_wfov"] = {"ms": round(ms3, 4), "points": int(nfused.value), "hypotheses": 1000, "inliers": int(ninl.value),
+                                            "fp64_tflops": round(flops / (ms3 * 1e-3) / 1e12, 2), "fp64_peak_tflops_nominal": round(fp64_peak, 1),
+                                            "frac_of_fp64_peak": round(flops / (ms3 * 1e-3) / 1e12 / fp64_peak, 3),
+                                            "note": "7 N H flop (3 mul + 3 add + compare per plane test, in f64 without contraction); the call includes the fit, "
+                                                    "the host replay of the best / early-exit rule, the inlier mask and the refit"}
+            del xyz, comp, dtab
+
     if rank == 0:
         peak, peak_src = peaks()
-        # per-kernel-family device time (CUDA events on each worker stream, inside the timed region)
-        fam = {k: v for k, v in prof.items()}
-        tot_ms = sum(v["ms"] for v in fam.values()) or 1.0
+        fam = dict(prof)
+        algo = family_bytes(stats, cfg, S, P) if stats else {}
+        leaf_ms = sum(v["ms"] for k, v in fam.items() if k in LEAF) or 1.0
         table = {}
         for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
-            gbs = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0
-            table[k] = {"ms_per_frame": round(v["ms"] / prof_frames, 4), "share": round(v["ms"] / tot_ms, 4),
-                        "calls": v["calls"], "algorithmic_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
-        # the dominant KERNEL: profile scopes nest (sor_knn / normals / icp wrap their own launch groups), so the
-        # roofline line is taken over the leaf families, each of which is one kernel (or one kernel per pass)
-        LEAF_KERNEL = {"knn_level0": "k_knn_hist", "knn_level1": "k_knn_wbf", "knn_stragglers": "k_knn", "icp": "k_icp_iter",
-                       "radix_sort": "k_rs_scatter", "ransac_score": "k_ransac_score", "unproject_transform": "k_unproject",
-                       "voxel_mean": "k_voxel_mean", "voxel_keys": "k_voxel_keys", "grid_keys": "k_grid_keys",
-                       "grid_hash": "k_grid_insert", "compact_gather": "k_gather3", "compact_scan": "k_flag_compact",
-                       "run_heads": "k_flag_compact", "sor_stats": "k_csum_level", "bounds": "k_bounds"}
-        top = next((k for k in table if k in LEAF_KERNEL), None)
+            if k not in LEAF:
+                continue                      # (sor / floor_sor / normals / icp_branch are scopes around their leaf families)
+            per_frame_ms = v["ms"] / prof_frames
+            gbs = algo.get(k, 0.0) / (per_frame_ms * 1e-3) / 1e9 if per_frame_ms > 0 else 0.0
+            table[k] = {"ms_per_frame": round(per_frame_ms, 4), "share": round(v["ms"] / leaf_ms, 4), "launch_groups": v["calls"],
+                        "kernel": LEAF[k][0], "bound": LEAF[k][1], "algorithmic_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
+        top = next(iter(table), None)
         roofline = None
         if top:
-            v = fam[top]
-            ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9
-            # launches inside one call of the family (ICP: one per executed pass; others: 1)
-            per_call = 1.0
-            if top == "icp":
-                per_call = float(np.mean([int(last[0].icp_iters[i]) + 1 for i in range(2)]))
-            traffic, traffic_src = None, None
+            t = table[top]
+            ncu = {}
             try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-                hits = [e for name, e in tj.items() if name.startswith(LEAF_KERNEL[top])]
-                if hits:
-                    traffic = float(np.mean([e["dram_bytes_per_launch"] for e in hits]))
-                    traffic_src = "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean over %d launches)" % sum(e["launches"] for e in hits)
+                ncu = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json"))).get(t["kernel"], {})
             except Exception:
                 pass
-            n_launch = max(v["calls"], 1) * per_call
-            roofline = {"kernel": LEAF_KERNEL[top], "family": top, "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
-                        "frac": round(ach / peak, 5), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                        "avg_launch_ms": round(v["ms"] / n_launch, 4), "algorithmic_bytes_per_launch": round(v["bytes"] / n_launch),
-                        "note": "dominant kernel by summed device time (CUDA events on the launching stream, one frame in flight). "
-                                "The neighbour search moves its compulsory bytes (cell-sorted float4 cloud in, one mean out) in a "
-                                "fraction of its run time: it is bound by instruction issue / latency (ncu: 48-59 % issue-active at 18-34 % occupancy, "
-                                "L1 hit rate 74-78 %, DRAM < 1 % busy), not by HBM; frac is reported against the HBM peak as the "
-                                "contract asks. HBM-bound kernels and their fractions are in `kernels`."}
+            launches_per_frame = {"knn_level0": 3.0, "icp": 1.0}.get(top, 1.0)
+            if top == "icp":
+                launches_per_frame = float(np.mean([int(last[0].icp_iters[i]) + 1 for i in range(2)]))
+            ach = t["algorithmic_GBps"]
+            roofline = {"kernel": t["kernel"], "family": top, "bound": t["bound"], "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": round(ach / peak, 5), "traffic": ncu.get("dram_bytes_per_launch"), "traffic_source": ncu.get("source"),
+                        "peak_source": peak_src, "avg_launch_ms": round(t["ms_per_frame"] / launches_per_frame, 4),
+                        "algorithmic_bytes_per_launch": round(algo.get(top, 0.0) / launches_per_frame),
+                        "issue_active_frac": ncu.get("issue_active_frac"), "warp_instructions_per_launch": ncu.get("warp_instructions_per_launch"),
+                        "note": "dominant kernel by summed device time (CUDA events around every kernel family, one batch in flight). "
+                                "It is bound by instruction issue, not by HBM: `achieved` / `frac` are its compulsory bytes over its run time against the "
+                                "HBM peak, as the contract asks; `issue_active_frac` (ncu, profiles/) is the fraction of its real ceiling. "
+                                "HBM-bound families and their fractions are in `kernels`."}
         cb = None
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(cfg, depth, tab, T_fuse, T_icp, args.cpu_sample_frames)
@@ -406,12 +496,14 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config,
-            "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": round(wall, 3),
+            "clocks": clocks, "gpu_launches": int(launches), "launches_per_frame": round(launches / max(B * args.steps, 1), 1),
+            "wall_s_timed_region": round(wall, 3),
             "e2e": None if e2e is None else {"value": frames_total / (ms_e2e_max * 1e-3), "unit": UNIT,
                                              "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                                              "ms_per_step": ms_e2e_max / args.steps},
-            "roofline": roofline, "kernels": table, "kernels_note": "per-family device time with one frame in flight "
-            "(serial ms/frame %.3f); the timed region overlaps %d frames" % (ms_serial / prof_frames, args.streams),
+            "roofline": roofline, "kernels": table,
+            "kernels_note": "per-family device time with %d frames per launch (as in the timed region) and ONE batch in flight, CUDA events around "
+                            "every family (serial ms/frame %.3f); the timed region overlaps %d such batches" % (fpl, ms_serial / prof_frames, slots),
             "cpu_baseline": cb,
             "frame_stats": {"n_fused": int(r0.n_fused), "n_voxel": int(r0.n_voxel), "n_sor": int(r0.n_sor),
                             "n_floor_inliers": int(r0.n_floor_inliers), "n_out": int(r0.n_out),
@@ -420,11 +512,12 @@ def main():
         }
         icpv = fam.get("icp")
         if icpv:
-            line["icp_ms_per_pair"] = round(icpv["ms"] / max(icpv["calls"], 1), 4)
+            line["icp_ms_per_pair"] = round(icpv["ms"] / prof_frames / 2, 4)
+            line["icp_ms_per_pair_note"] = "WFOV pair inside C4 (one frame per launch); the NFOV pair of config C2 is legs.C2_nfov_icp"
         if c5 is not None:
             line["resample_c5"] = c5
-        if k1b:
-            line["k1_batched"] = k1b
+        if legs:
+            line["legs"] = legs
         print(json.dumps(line))
     pipe.close()
     if world > 1:

@@ -112,6 +112,7 @@ SIGNATURES = {
     "kp_pipeline_run": (C.c_int, [_vp, _vp, C.c_int, _i64, C.POINTER(FrameResult), _vp, _i64]),
     "kp_pipeline_launch_count": (_i64, [_vp]),
     "kp_pipeline_frames_in_flight": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "kp_pipeline_frame_counts": (C.c_int, [_vp, _pi64, C.c_int]),
     "kp_pipeline_profile": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_char_p), _pf64, _pi64, _pf64, C.POINTER(C.c_int)]),
     "kp_pipeline_run_host": (C.c_int, [_vp, _vp, _i64, C.POINTER(FrameResult), _vp, _i64]),
 }

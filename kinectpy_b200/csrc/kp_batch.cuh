@@ -118,7 +118,7 @@ int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, 
 int kp_knn_batch_vbi(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows);
 void kp_knn_batch_destroy(KpKnnBatch *b);
 int kp_knn_batch_level0(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows);
-int kp_knn_batch_level1(kp_ctx *ctx, const KpKnnBatch &b);
+int kp_knn_batch_level1(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows);
 int kp_knn_batch_stragglers(kp_ctx *ctx, const KpKnnBatch &b);
 
 // ---- batched point-to-plane ICP (kp_icp.cu): every pair of the batch advances in the same launches

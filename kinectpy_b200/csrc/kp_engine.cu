@@ -777,7 +777,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_e_ransac_score(const __grid_c
         __syncthreads();
     }
 }
-// Open3D's sequential best / early-exit rule replayed over the H counts (oracle: kpo_ransac_plane).  The evolution
+// Open3D's sequential best / early-exit rule replayed over the H counts.  The evolution
 // of (best fitness, early-exit bound, processed set) does not depend on how ties are broken, only the winner
 // among the hypotheses that tie on the final best count does: those are listed for the tie pass.
 __global__ void k_e_ransac_select(const __grid_constant__ RansacArgs a)
@@ -1190,7 +1190,7 @@ int stage_knn(kp_pipeline *pl, kp_ctx *ctx, const KnnStage &k, int nseg, int64_t
     KP_TRY(kp_b_compact_index(L, sc, k.n, k.flags0, k.flag_stride, k.list0, k.list_stride, k.cnt0));
     KP_TRY(stage_grid(pl, ctx, k.coarse, nseg, cap_rows, sc, sink));
     KP_CUDA(ctx, cudaMemsetAsync(k.flags1, 0, (size_t)nseg * k.flag_stride, ctx->stream));
-    KP_TRY(kp_knn_batch_level1(ctx, *k.batch));
+    KP_TRY(kp_knn_batch_level1(ctx, *k.batch, cap_rows));
     KP_TRY(kp_b_compact_index(L, sc, k.n, k.flags1, k.flag_stride, k.list1, k.list_stride, k.cnt1));
     KP_TRY(kp_knn_batch_stragglers(ctx, *k.batch));
     return KP_OK;
@@ -1819,6 +1819,26 @@ int kp_pipeline_frames_in_flight(kp_pipeline *p, int *batch, int *slots)
     if (!p) return KP_E_ARG;
     if (batch) *batch = p->B;
     if (slots) *slots = p->W;
+    return KP_OK;
+}
+
+int kp_pipeline_frame_counts(kp_pipeline *p, int64_t *h_counts, int n)
+{
+    // the device-side counts of the first frame of batch slot 0 after its last batch (diagnostics / byte accounting):
+    // n_fused, n_voxel, n_sor, n_lo, n_rest, n_merged, n_fsor, n_out, level-0 leftovers [3], level-1 leftovers [3],
+    // valid rows of the S ICP inputs [6], their voxel counts [6]
+    if (!p || !h_counts || n < 26) return KP_E_ARG;
+    cudaSetDevice(p->device);
+    EngSlot &s = p->slots[0];
+    if (cudaStreamSynchronize(s.ctx->stream) != cudaSuccess) return KP_E_CUDA;
+    EngDyn d;
+    if (cudaMemcpy(&d, s.dyn, sizeof d, cudaMemcpyDeviceToHost) != cudaSuccess) return KP_E_CUDA;
+    std::vector<EngCloud> cl((size_t)p->cfg.S);
+    if (cudaMemcpy(cl.data(), s.icl, sizeof(EngCloud) * cl.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return KP_E_CUDA;
+    const int64_t v[8] = {d.n_fused, d.n_voxel, d.n_sor, d.n_lo, d.n_rest, d.n_merged, d.n_fsor, d.n_out};
+    for (int i = 0; i < 8; ++i) h_counts[i] = v[i];
+    for (int i = 0; i < 3; ++i) { h_counts[8 + i] = d.cnt_l0[i]; h_counts[11 + i] = d.cnt_l1[i]; }
+    for (int i = 0; i < 6; ++i) { h_counts[14 + i] = i < p->cfg.S ? cl[i].nv : 0; h_counts[20 + i] = i < p->cfg.S ? cl[i].n : 0; }
     return KP_OK;
 }
 

@@ -1003,8 +1003,10 @@ __global__ void __launch_bounds__(HQT) k_knn_hist_b(const __grid_constant__ KnnB
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const KnnParams &p = a.p[blockIdx.y];
     const KpGridDev g = *p.gdev;
-    const int64_t nq = *p.nq_dev;
-    for (int64_t w = (int64_t)blockIdx.x * HQT + threadIdx.x; w < nq; w += (int64_t)gridDim.x * HQT) hq_query<NB, R, HQT>(p, g, w, smem_raw);
+    // level 0: every point of the cloud; coarser levels: the positions the level before could not certify (qlist)
+    const int64_t nq = p.qlist ? (int64_t)*p.qcount : (int64_t)*p.nq_dev;
+    for (int64_t w = (int64_t)blockIdx.x * HQT + threadIdx.x; w < nq; w += (int64_t)gridDim.x * HQT)
+        hq_query<NB, R, HQT>(p, g, p.qlist ? (int64_t)p.qlist[w] : w, smem_raw);
 }
 
 // ---- the same histogram select over the voxel-brick index (kp_vbi.cuh) of a voxel-downsampled cloud.
@@ -1659,7 +1661,7 @@ int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, 
         h[s] = a;
         // level 1: the level-0 leftovers (list0), one warp each, against the coarse grid
         KnnParams b = p;
-        b.cap = out->cap_hist; b.gdev = d.g1; b.qlist = d.list0; b.qcount = d.cnt0; b.strag_flags = d.flags1;
+        b.cap = out->cap_hist; b.gdev = d.g1; b.qlist = d.list0; b.qcount = d.cnt0; b.strag_flags = d.flags1; b.rad = 1;
         h[(size_t)nseg + s] = b;
         // stragglers: ring expansion on the coarse grid
         KnnParams c = p;
@@ -1694,9 +1696,9 @@ void kp_knn_batch_destroy(KpKnnBatch *b)
     if (b && b->h_params) { free(b->h_params); b->h_params = nullptr; }
 }
 template <int NB, int R, int T>
-static int knn_level0_launch(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows, int per_sm)
+static int knn_level0_launch(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows, int per_sm, int level = 0)
 {
-    const KnnParams *hp = (const KnnParams *)b.h_params;
+    const KnnParams *hp = (const KnnParams *)b.h_params + (size_t)level * b.nseg;
     const size_t smem = (size_t)T * ((size_t)b.cap_hist * 8 + NB * 2);
     int64_t gx = (cap_rows + T - 1) / T;
     if (gx > (int64_t)ctx->sm_count * per_sm) gx = (int64_t)ctx->sm_count * per_sm;
@@ -1713,8 +1715,10 @@ static int knn_level0_launch(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows,
 int kp_knn_batch_level0(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows)
 {
     KP_PROFB(ctx, "knn_level0", 0.0);
-    if (b.k <= 32) return b.rad == 2 ? knn_level0_launch<32, 2, 128>(ctx, b, cap_rows, 24) : knn_level0_launch<32, 1, 128>(ctx, b, cap_rows, 24);
-    return b.rad == 2 ? knn_level0_launch<64, 2, 64>(ctx, b, cap_rows, 32) : knn_level0_launch<64, 1, 64>(ctx, b, cap_rows, 32);
+    // persistent CTAs per SM and segment (KP_KNN_CTAS): fewer leave registers for another batch's kernels on the same SM
+    static const int per_sm = getenv("KP_KNN_CTAS") ? atoi(getenv("KP_KNN_CTAS")) : 24;
+    if (b.k <= 32) return b.rad == 2 ? knn_level0_launch<32, 2, 128>(ctx, b, cap_rows, per_sm) : knn_level0_launch<32, 1, 128>(ctx, b, cap_rows, per_sm);
+    return b.rad == 2 ? knn_level0_launch<64, 2, 64>(ctx, b, cap_rows, per_sm * 4 / 3) : knn_level0_launch<64, 1, 64>(ctx, b, cap_rows, per_sm * 4 / 3);
 }
 int kp_knn_batch_vbi(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows)
 {
@@ -1736,12 +1740,21 @@ int kp_knn_batch_vbi(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows)
     KP_LAUNCH_CHECK(ctx);
     return KP_OK;
 }
-int kp_knn_batch_level1(kp_ctx *ctx, const KpKnnBatch &b)
+// level 1: the level-0 leftovers (compacted list), one warp each, best-first on the coarse grid
+int kp_knn_batch_level1(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows)
 {
     KP_PROFB(ctx, "knn_level1", 0.0);
-    k_knn_wbf_b<<<dim3((unsigned)ctx->sm_count * 8, (unsigned)b.nseg), WH_WARPS * 32, 0, ctx->stream>>>((const KnnParams *)b.d_params + b.nseg);
-    KP_LAUNCH_CHECK(ctx);
-    return KP_OK;
+    // measured: the histogram kernel on the coarse grid (KP_KNN_L1=hist) certifies only ~half of the leftovers (one bin of
+    // the 9x larger range holds more candidates than the buffer) at 2.8x the time of the best-first kernel: kept as an option
+    static const bool wbf = !(getenv("KP_KNN_L1") && !strcmp(getenv("KP_KNN_L1"), "hist"));
+    if (wbf) {
+        k_knn_wbf_b<<<dim3((unsigned)ctx->sm_count * 8, (unsigned)b.nseg), WH_WARPS * 32, 0, ctx->stream>>>((const KnnParams *)b.d_params + b.nseg);
+        KP_LAUNCH_CHECK(ctx);
+        return KP_OK;
+    }
+    // (a fraction of the cloud reaches this level: a quarter of the level-0 grid is plenty)
+    if (b.k <= 32) return knn_level0_launch<32, 1, 128>(ctx, b, cap_rows / 4 + 1, 8, 1);
+    return knn_level0_launch<64, 1, 64>(ctx, b, cap_rows / 4 + 1, 8, 1);
 }
 int kp_knn_batch_stragglers(kp_ctx *ctx, const KpKnnBatch &b)
 {

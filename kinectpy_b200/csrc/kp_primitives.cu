@@ -239,14 +239,18 @@ int compact_generic(kp_ctx *ctx, int64_t n, Flag flag, Emit emit, int32_t *d_tot
         return KP_OK;
     }
     unsigned nb = kp_blocks(n, SC_TILE);
-    if (nb <= (unsigned)kp_ctx::LB_TILES) {
+    // The single-pass kernel numbers its tiles by blockIdx.x and a tile waits for the words of the tiles before it: that
+    // only makes progress if every earlier tile has started, which is guaranteed while the whole grid is resident (four
+    // CTAs of 256 threads per SM fit in every configuration of this kernel) and merely customary beyond that.  Larger
+    // arrays take the count / scan / scatter path below, where no CTA waits for another one.
+    if (nb <= (unsigned)kp_ctx::LB_TILES && nb <= (unsigned)ctx->sm_count * 4u) {
         unsigned epoch;
         KP_TRY(lb_next_epoch(ctx, &epoch));
         k_flag_compact<<<nb, SC_THREADS, 0, ctx->stream>>>(n, flag, emit, ctx->d_lb_state, epoch, d_total);
         KP_LAUNCH_CHECK(ctx);
         return KP_OK;
     }
-    // more tiles than look-back words: count / scan / scatter
+    // more tiles than are resident at once: count / scan / scatter
     int32_t *d_sums;
     KP_TRY(kp_ws(ctx, nb, &d_sums));
     k_flag_count<<<nb, SC_THREADS, 0, ctx->stream>>>(n, flag, d_sums);

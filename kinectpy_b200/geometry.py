@@ -49,12 +49,29 @@ class _Attr:
     def present(self) -> bool:
         return self.n > 0 and (self.host is not None or self.dev is not None)
 
-    def device(self, ctx) -> Optional[DeviceArray]:
+    def device(self, ctx, points: bool = False) -> Optional[DeviceArray]:
         if not self.present():
             return None
         if self.dev is None:
-            self.dev = ctx.to_device(self.host, dtype=np.float32)
+            h = self.host
+            if points:
+                # device convention: a row whose x is NaN is absent.  A row with ANY non-finite component (NaN in y or z,
+                # an infinity) is uploaded as an all-NaN row, so every kernel skips it and remove_non_finite_points drops
+                # it -- what Open3D's RemoveNonFinitePoints does; the host array is not modified
+                bad = ~np.isfinite(h).all(axis=1)
+                if bad.any():
+                    h = h.copy()
+                    h[bad] = np.nan
+            self.dev = ctx.to_device(h, dtype=np.float32)
         return self.dev
+
+    def peek_host(self) -> np.ndarray:
+        """Host copy for READING: the device copy stays valid (internal callers that do not edit the array)."""
+        if self.host is not None:
+            return self.host
+        if self.dev is None or self.n == 0:
+            return np.zeros((0, 3), dtype=np.float64)
+        return self.dev.to_host(self.n).astype(np.float64)
 
     def to_host(self) -> np.ndarray:
         if self.host is None:
@@ -93,7 +110,7 @@ class PointCloud:
 
     def _dev(self):
         ctx = self._ctx
-        return ctx, self._p.device(ctx), self._c.device(ctx), self._n.device(ctx)
+        return ctx, self._p.device(ctx, points=True), self._c.device(ctx), self._n.device(ctx)
 
     @staticmethod
     def _ptr(d: Optional[DeviceArray]):
@@ -266,11 +283,22 @@ class PointCloud:
         return out, (idx.to_host(cnt.value) if want_index else None)
 
     def select_by_index(self, indices, invert: bool = False) -> "PointCloud":
-        """``select_by_index`` (floor_removal.py:50,69,71,72): output in ascending index order."""
+        """``select_by_index`` (floor_removal.py:50,69,71,72).  The reference passes ascending, unique index lists
+        (the results of ``remove_statistical_outlier`` / ``segment_plane``); those go through a mask and an ordered
+        compaction on the device.  Any other list (unsorted, repeated indices) is gathered in the order given, as
+        Open3D does; ``invert`` ignores order and repetition by definition."""
         n = self._p.n
         idx = np.asarray(indices, dtype=np.int64).reshape(-1)
         if idx.size and (idx.min() < 0 or idx.max() >= n):
             raise KinectPyB200Error(_cabi.KP_E_ARG, "select_by_index: index out of range")
+        if not invert and idx.size > 1 and not bool(np.all(idx[1:] > idx[:-1])):
+            out = PointCloud(device=self._device)
+            out._p.set_host(self._p.peek_host()[idx].copy())
+            if self.has_colors():
+                out._c.set_host(self._c.peek_host()[idx].copy())
+            if self.has_normals():
+                out._n.set_host(self._n.peek_host()[idx].copy())
+            return out
         mask = np.zeros(n, dtype=np.uint8)
         mask[idx] = 1
         if n == 0:
@@ -403,8 +431,8 @@ class TransformationEstimationPointToPoint:
         ``manual_pointcloud_registration.py:90-92``: Umeyama / Kabsch over a handful of hand-picked pairs
         (host-side; three to a dozen points are not device work)."""
         c = np.asarray(corres).astype(np.int64).reshape(-1, 2)
-        s = np.asarray(source.points, dtype=np.float64)[c[:, 0]]
-        t = np.asarray(target.points, dtype=np.float64)[c[:, 1]]
+        s = source._p.peek_host()[c[:, 0]]          # (read-only: the device copies stay valid)
+        t = target._p.peek_host()[c[:, 1]]
         T = np.eye(4)
         if len(c) == 0:
             return T
@@ -623,8 +651,8 @@ def registration_ransac_based_on_feature_matching(source: PointCloud, target: Po
     # correspondence_set of the result: the correspondences the winning transform brings within the threshold
     inl = corres[:0]
     if fit.value > 0 and len(corres):
-        sp = np.asarray(source.points)[corres[:, 0]] @ T[:3, :3].T + T[:3, 3]
-        d2 = ((sp - np.asarray(target.points)[corres[:, 1]]) ** 2).sum(axis=1)
+        sp = source._p.peek_host()[corres[:, 0]] @ T[:3, :3].T + T[:3, 3]     # (read-only: no re-upload on the next trial)
+        d2 = ((sp - target._p.peek_host()[corres[:, 1]]) ** 2).sum(axis=1)
         inl = corres[d2 < max_correspondence_distance ** 2]
     res = RegistrationResult(T, fit.value, rmse.value, int(best.value), len(inl), inl)
     res.num_validated = int(val.value)

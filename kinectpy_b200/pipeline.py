@@ -171,6 +171,19 @@ class FramePipeline:
         self.lib.kp_pipeline_frames_in_flight(self.handle, C.byref(b), C.byref(w))
         return b.value, w.value
 
+    def frame_counts(self) -> dict:
+        """Device-side counts of the first frame of the last batch on slot 0 (diagnostics, byte accounting)."""
+        v = (C.c_int64 * 26)()
+        rc = self.lib.kp_pipeline_frame_counts(self.handle, v, 26)
+        if rc != 0:
+            self._raise(rc)
+        S = self.cfg.n_sensors
+        d = dict(zip(("n_fused", "n_voxel", "n_sor", "n_lo", "n_rest", "n_merged", "n_fsor", "n_out"), [int(x) for x in v[:8]]))
+        d["n_inl"] = d["n_lo"] - d["n_rest"]
+        d["leftovers_l0"], d["leftovers_l1"] = [int(x) for x in v[8:11]], [int(x) for x in v[11:14]]
+        d["nv_icp"], d["n_icp"] = [int(x) for x in v[14:14 + S]], [int(x) for x in v[20:20 + S]]
+        return d
+
     def launch_count(self) -> int:
         return int(self.lib.kp_pipeline_launch_count(self.handle))
 

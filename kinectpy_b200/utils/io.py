@@ -13,6 +13,7 @@ import ctypes as C
 import numpy as np
 
 from .. import _cabi
+from .._cabi import KinectPyB200Error
 from ..geometry import PointCloud
 
 COLOR_SUFFIX = '_rgb.png'
@@ -45,7 +46,15 @@ def rgbd_to_pointcloud(color_img, depth_img, keep_mask=None, transform=None) -> 
     ``keep_mask`` (uint8 per pixel) and ``transform`` (4x4) are extensions used by the crop / fusion
     callers so that the mask, the extrinsic and the compaction stay in one pass on the device.
     """
-    xyz16 = np.ascontiguousarray(np.asarray(depth_img).reshape(-1, 3), dtype=np.int16)
+    raw = np.asarray(depth_img).reshape(-1, 3)
+    if raw.dtype != np.int16:
+        # the reference casts to float64 (utils/io.py:29); the device path is the int16 `_depth.dat` layout: anything that
+        # is not exactly representable there is refused instead of being wrapped or truncated silently
+        as16 = raw.astype(np.int16)
+        if not np.array_equal(as16.astype(np.float64), raw.astype(np.float64)):
+            raise KinectPyB200Error(_cabi.KP_E_ARG, "rgbd_to_pointcloud: depth_img holds values that are not int16 XYZ millimetres")
+        raw = as16
+    xyz16 = np.ascontiguousarray(raw, dtype=np.int16)
     n = xyz16.shape[0]
     if n == 0:
         return PointCloud()

@@ -252,6 +252,12 @@ def main():
         T = ref_registration.execute_point_to_plane_registration(PointCloud(master), PointCloud(sub), init, voxel_size=35)
     out["reg_master"], out["reg_sub"], out["reg_init"], out["reg_T"] = master, sub, init, np.asarray(T, np.float64)
     out["reg_calls"] = np.array(repr(CALLS))
+    # the wrappers' own source text (fixture data, like floor_source / fuse_source below): tests/test_gpu_dropin.py executes
+    # it, unmodified, over kinectpy_b200.o3d on the GPU box, where /root/reference does not exist
+    import inspect
+    out["fo_source"] = np.array(inspect.getsource(ref_filtering.filter_outliers))
+    out["reg_source"] = np.array("\n".join(inspect.getsource(f) for f in (ref_registration.preprocess_point_cloud, ref_registration.prepare_dataset,
+                                                                          ref_registration.execute_point_to_plane_registration)))
 
     # ---- floor removal: the body of the script's loop, exec'd verbatim from the reference's file
     src_lines = open(os.path.join(REF, "floor_removal.py")).read().splitlines()

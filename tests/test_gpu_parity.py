@@ -115,10 +115,11 @@ def test_transform_bounds_compact(ctx, oracle):
 
 
 
-@pytest.mark.parametrize("n", [1, 31, 2047, 2048, 2049, 65536, 300007])
+@pytest.mark.parametrize("n", [1, 31, 2047, 2048, 2049, 65536, 300007, 1300003, 6000011])
 def test_compact_single_pass_scan_across_tiles(ctx, n):
     """Ordered compaction is one kernel: tiles of 2048 whose offsets come from published tile aggregates and group
-    totals (groups of 32 tiles), each word tagged with a per-call epoch (never cleared).  Ragged sizes around the tile
+    totals (groups of 32 tiles), each word tagged with a per-call epoch (never cleared) -- while the grid is resident at
+    once (<= 4 CTAs per SM); larger arrays (the last two sizes) take the count / scan / scatter path.  Ragged sizes around the tile
     and group edges, sparse / dense / run-structured masks, and back-to-back calls on the same context (stale words
     of earlier calls must read as 'not ready')."""
     rng = np.random.default_rng(n)

@@ -127,3 +127,32 @@ def test_rgbd_to_pointcloud_and_formats(oracle, tmp_path):
     back = o3d.io.read_point_cloud(out)
     assert np.array_equal(f32(back.points), f32(pcd.points)) and back.has_colors()
     assert np.abs(np.asarray(back.colors) - np.asarray(pcd.colors)).max() <= 1 / 255 + 1e-6
+
+
+def test_select_by_index_keeps_the_given_order_and_non_finite_rows_are_absent():
+    """(i) an unsorted / repeated index list is gathered in the order given, like Open3D (ascending unique
+    lists -- what the reference passes -- go through the mask + ordered compaction path); (ii) a row with ANY non-finite
+    component is absent on the device and dropped by remove_non_finite_points; (iii) rgbd_to_pointcloud refuses depth
+    values that are not int16 instead of wrapping them."""
+    from kinectpy_b200 import _cabi
+    from kinectpy_b200.geometry import PointCloud
+    from kinectpy_b200.utils.io import rgbd_to_pointcloud
+    pts = np.random.default_rng(5).random((100, 3))
+    pc = PointCloud(pts)
+    idx = [7, 3, 3, 50, 0]
+    assert np.allclose(np.asarray(pc.select_by_index(idx).points), pts[idx].astype(np.float32))
+    asc = [0, 3, 7, 50]
+    assert np.allclose(np.asarray(pc.select_by_index(asc).points), pts[asc].astype(np.float32))
+    assert len(pc.select_by_index(idx, invert=True).points) == 100 - 4
+    bad = pts.copy()
+    bad[3, 1] = np.nan
+    bad[10, 2] = np.inf
+    bad[20, 0] = -np.inf
+    pb = PointCloud(bad)
+    down = pb.voxel_down_sample(1e-3)                     # every finite point its own voxel
+    assert len(down.points) == 97 and np.isfinite(np.asarray(down.points)).all()
+    assert len(PointCloud(bad).remove_non_finite_points().points) == 97
+    with pytest.raises(_cabi.KinectPyB200Error):
+        rgbd_to_pointcloud(None, np.array([[1.0, 2.0, 70000.0]]))
+    ok = rgbd_to_pointcloud(None, np.array([[1.0, 2.0, 300.0], [0.0, 5.0, 6.0]]))
+    assert len(ok.points) == 1
