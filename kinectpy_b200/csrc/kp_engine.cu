@@ -140,16 +140,31 @@ __global__ void __launch_bounds__(256) k_e_voxel_keys(const __grid_constant__ Vo
     const KpVoxDev vp = vox_of(a.vp, a.vp_stride, seg);
     const float *xyz = a.xyz + 3 * seg * a.xyz_stride;
     uint32_t *keys = a.keys + seg * a.key_stride;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
-        uint32_t key = vp.sentinel;
-        if (vp.ok && !isnan(x)) {
-            const long long ix = (long long)floor(__ddiv_rn(__dsub_rn((double)x, vp.minb[0]), vp.voxel));
-            const long long iy = (long long)floor(__ddiv_rn(__dsub_rn((double)y, vp.minb[1]), vp.voxel));
-            const long long iz = (long long)floor(__ddiv_rn(__dsub_rn((double)z, vp.minb[2]), vp.voxel));
-            key = (uint32_t)(((unsigned long long)ix << vp.sh_x) | ((unsigned long long)iy << vp.sh_y) | (unsigned long long)iz);
+    // four rows per thread and trip, all twelve loads issued before the first division: the kernel is a stream of
+    // 12-byte rows in and 4-byte keys out, and the three IEEE double divisions per row are latency, not throughput
+    constexpr int U = 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < a.n; i0 += U * stride) {
+        float x[U], y[U], z[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            x[u] = NAN; y[u] = 0.f; z[u] = 0.f;
+            if (i < a.n) { x[u] = xyz[3 * i]; y[u] = xyz[3 * i + 1]; z[u] = xyz[3 * i + 2]; }
         }
-        keys[i] = key;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= a.n) break;
+            uint32_t key = vp.sentinel;
+            if (vp.ok && !isnan(x[u])) {
+                const long long ix = (long long)floor(__ddiv_rn(__dsub_rn((double)x[u], vp.minb[0]), vp.voxel));
+                const long long iy = (long long)floor(__ddiv_rn(__dsub_rn((double)y[u], vp.minb[1]), vp.voxel));
+                const long long iz = (long long)floor(__ddiv_rn(__dsub_rn((double)z[u], vp.minb[2]), vp.voxel));
+                key = (uint32_t)(((unsigned long long)ix << vp.sh_x) | ((unsigned long long)iy << vp.sh_y) | (unsigned long long)iz);
+            }
+            keys[i] = key;
+        }
     }
 }
 // one thread per voxel run: sums its points in input order (the sort is stable) in double, one division, one rounding

@@ -997,8 +997,11 @@ __global__ void __launch_bounds__(HQT) k_knn_hist(const __grid_constant__ KnnPar
 // count, which an earlier kernel of the frame produced, are loaded from device memory into registers
 constexpr int KNN_ARG_SEGS = 8;
 struct KnnBatchArgs { KnnParams p[KNN_ARG_SEGS]; };
+#ifndef KNN_MIN_CTAS_T
+#define KNN_MIN_CTAS_T 0
+#endif
 template <int NB, int R, int HQT>
-__global__ void __launch_bounds__(HQT) k_knn_hist_b(const __grid_constant__ KnnBatchArgs a)
+__global__ void __launch_bounds__(HQT, KNN_MIN_CTAS_T > 0 ? KNN_MIN_CTAS_T / HQT : 1) k_knn_hist_b(const __grid_constant__ KnnBatchArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const KnnParams &p = a.p[blockIdx.y];

@@ -34,11 +34,31 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 // reused for every frame of the batch; depth streams through with one 128-bit load per thread.
 // Compile-time variants (k4a int16 rounding, drop-any-zero rule, extrinsic, bounds) so a launch carries only its
 // own arithmetic: the flag tests and the dead branches they guard were a fifth of the instructions.
+// rows of a warp's 256 pixels through a warp-private shared-memory stage: every lane parks its 24 floats (row stride
+// 25: conflict-free), then the warp writes them back out as six fully coalesced 512-byte float4 rows.  (The direct
+// form -- every lane storing its own 96 contiguous bytes -- half-fills 32 sectors per store instruction.)  Only a
+// __syncwarp on either side: no CTA barrier in the frame loop.
+__device__ __forceinline__ void up_store_rows(float *stage, const float *vals, float *dst_warp, int lane)
+{
+#pragma unroll
+    for (int j = 0; j < UP_PPT * 3; ++j) stage[lane * 25 + j] = vals[j];
+    __syncwarp();
+    float4 *d4 = reinterpret_cast<float4 *>(dst_warp);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const int e0 = 4 * (32 * k + lane);
+        const float *sp = stage + (e0 / 24) * 25 + (e0 % 24);
+        d4[32 * k + lane] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+    }
+    __syncwarp();
+}
+
 template <bool INT16, bool DROP, bool HAS_T, bool BOUNDS, bool RAW = false>
-__global__ void __launch_bounds__(UP_THREADS, 3) k_unproject(const __grid_constant__ UnprojParams p)
+__global__ void __launch_bounds__(UP_THREADS, RAW ? 2 : 3) k_unproject(const __grid_constant__ UnprojParams p)
 {
     __shared__ __align__(128) float2 tab_s[UP_TILE];
     __shared__ __align__(8) uint64_t mbar;
+    __shared__ float stage_s[UP_THREADS / 32][32 * 25];
     const int tid = threadIdx.x, lane = tid & 31;
     const int s = blockIdx.y;
     const int64_t p0 = (int64_t)blockIdx.x * UP_TILE;
@@ -161,7 +181,10 @@ __global__ void __launch_bounds__(UP_THREADS, 3) k_unproject(const __grid_consta
             }
         }
         float *o = p.xyz + 3 * row;
-        if (full && vst_ok) {
+        const bool tile_full = npx == UP_TILE;          // CTA-uniform: every lane of every warp owns 8 pixels
+        if (tile_full && vst_ok) {
+            up_store_rows(stage_s[tid >> 5], out, o - 3 * (lane * UP_PPT), lane);
+        } else if (full && vst_ok) {
             float4 *o4 = reinterpret_cast<float4 *>(o);
 #pragma unroll
             for (int q = 0; q < 6; ++q) o4[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
@@ -172,7 +195,9 @@ __global__ void __launch_bounds__(UP_THREADS, 3) k_unproject(const __grid_consta
         }
         if (RAW) {
             float *r = p.xyz_raw + 3 * row;
-            if (full && vst_ok && ((((uintptr_t)p.xyz_raw) & 15u) == 0u)) {
+            if (tile_full && vst_ok && ((((uintptr_t)p.xyz_raw) & 15u) == 0u)) {
+                up_store_rows(stage_s[tid >> 5], raw, r - 3 * (lane * UP_PPT), lane);
+            } else if (full && vst_ok && ((((uintptr_t)p.xyz_raw) & 15u) == 0u)) {
                 float4 *r4 = reinterpret_cast<float4 *>(r);
 #pragma unroll
                 for (int q = 0; q < 6; ++q) r4[q] = make_float4(raw[4 * q], raw[4 * q + 1], raw[4 * q + 2], raw[4 * q + 3]);

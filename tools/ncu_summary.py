@@ -25,7 +25,9 @@ def main(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = rows[0]
+    units = rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
+    tscale = {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6, "s": 1e6}
     name_i = idx.get("Kernel Name")
     for r in rows[2:]:
         if len(r) < len(hdr):
@@ -34,6 +36,10 @@ def main(path):
         for k, short, sc in KEYS:
             if k in idx:
                 try:
+                    if short == "dur_us":
+                        sc = tscale.get(units[idx[k]], 1e-3)
+                    elif short.endswith("_MB"):
+                        sc = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(units[idx[k]], 1e-6)
                     vals[short] = round(float(r[idx[k]].replace(",", "")) * sc, 3)
                 except ValueError:
                     vals[short] = r[idx[k]]
