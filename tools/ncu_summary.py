@@ -22,7 +22,8 @@ KEYS = [
 STALL = "smsp__average_warp_latency_issue_stalled_"  # (raw page name prefix varies; fall back to pcsamp)
 
 def main(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a report (.ncu-rep: read through `ncu -i`) or the raw page already exported as CSV on the GPU box
+    out = open(path).read() if path.endswith(".csv") else subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = rows[0]
     units = rows[1]
