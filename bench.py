@@ -159,7 +159,7 @@ def cpu_baseline(cfg, depth, tab, T_fuse, T_icp, frames):
 # kernel family of the profile -> (dominant kernel, binding resource)
 LEAF = {
     "knn_level0": ("k_knn_hist_b", "issue"), "knn_level1": ("k_knn_wbf_b", "issue"), "knn_stragglers": ("k_knn_b", "issue"),
-    "knn_vbi": ("k_knn_vbi_b", "issue"), "icp": ("k_icp_iter_b", "issue"),
+    "knn_vbi": ("k_knn_vbi_b", "issue"), "knn_mid": ("k_knn_hist_b", "issue"), "icp": ("k_icp_iter_b", "issue"),
     "radix_sort": ("k_rs_scatter", "hbm"), "ransac_score": ("k_e_ransac_score", "fp64"), "ransac_fit": ("k_e_ransac_fit", "latency"),
     "ransac_select": ("k_e_ransac_select", "latency"),
     "unproject_transform": ("k_unproject", "hbm"), "voxel_mean": ("k_e_voxel_mean", "hbm"), "voxel_keys": ("k_e_voxel_keys", "hbm"),

@@ -103,13 +103,15 @@ struct KpKnnSegDesc {
     uint8_t *flags0, *flags1;     // [cap] "not certified at level 0 / 1", indexed by level-0 position
     int32_t *list0, *list1;       // [cap] compacted positions
     const int32_t *cnt0, *cnt1;   // device: lengths of the lists
+    const KpGridDev *gm;          // optional mid level (NULL = none): grid, flags, list and count of what it leaves
+    uint8_t *flags_m; int32_t *list_m; const int32_t *cnt_m;
     double *mean;                 // SOR: mean distance to the k nearest (by original index)
     const float *cloud;           // normals mode: the cloud, by original index
     float *normals;               // normals mode: output
 };
 struct KpKnnBatch {
     void *d_params = nullptr, *h_params = nullptr;     // [3 levels][nseg] parameter blocks on the device and their host copy
-    int nseg = 0, k = 0, mode = 0, cap_hist = 0, cap_warp = 0, rad = 1;
+    int nseg = 0, k = 0, mode = 0, cap_hist = 0, cap_warp = 0, rad = 1, cap_mid = 0, has_mid = 0;
 };
 // mode 0: mean distance of the k nearest (SOR); mode 1: normals from the <= k nearest inside `radius`
 // rho_a / rho_b: the two search radii of the voxel-brick level 0 (ignored without an index)
@@ -118,6 +120,7 @@ int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, 
 int kp_knn_batch_vbi(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows);
 void kp_knn_batch_destroy(KpKnnBatch *b);
 int kp_knn_batch_level0(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows);
+int kp_knn_batch_mid(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows);
 int kp_knn_batch_level1(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows);
 int kp_knn_batch_stragglers(kp_ctx *ctx, const KpKnnBatch &b);
 

@@ -37,11 +37,13 @@ struct EngDyn {
     int32_t status, floor_skip, ymax_enc, pad0;
     int32_t nocc[4];                    // occupied cells of grid g[0..3]
     int32_t cnt_l0[3], cnt_l1[3];       // level-0 / level-1 leftover lists of the three neighbour searches
+    int32_t cnt_lm[3], nocc_m[2], pad3; // leftovers of the mid level; occupied cells of the mid grids
     int32_t n_old[3], pad2;             // points the GRID level 0 has to search: 0 when the voxel-brick index was built
     int32_t ransac_best, ransac_ncand, ransac_cand[ENG_MAX_CAND];
     float b6[6];                        // bounds of the fused cloud
     KpVoxDev vox_fused;
     KpGridDev g[4];                     // [0],[1]: level 0 / 1 of the main branch, [2],[3]: of the ICP target
+    KpGridDev gm[2];                    // mid-level grids (main branch, ICP target)
     KpVbiDev vbi[2];                    // voxel-brick index: [0] main branch (SOR clouds), [1] ICP target
     double sor_sum, sor_sq, sor_stats[3];
     double plane[4];
@@ -95,7 +97,7 @@ __global__ void k_e_frame_setup(const __grid_constant__ SetupParams p, int B)
     d.status = KP_OK; d.floor_skip = 0; d.ymax_enc = kp_f2ord(-INFINITY);
     d.n_voxel = d.n_sor = d.n_lo = d.n_rest = d.n_merged = d.n_fsor = d.n_out = 0;
     d.ransac_best = -1; d.ransac_ncand = 0;
-    for (int i = 0; i < 3; ++i) { d.cnt_l0[i] = 0; d.cnt_l1[i] = 0; }
+    for (int i = 0; i < 3; ++i) { d.cnt_l0[i] = 0; d.cnt_l1[i] = 0; d.cnt_lm[i] = 0; }
     // fused bounds = union over the sensors that saw anything (set 0 rows)
     float b6[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
     int nvalid = 0;
@@ -1017,7 +1019,8 @@ struct EngSlot {
     BSort sortw{nullptr, nullptr};
     BScan scan{nullptr, nullptr, 0};
     float *A = nullptr, *Bb = nullptr, *C = nullptr, *D = nullptr, *E = nullptr, *Fin = nullptr;
-    float4 *sorted[2] = {nullptr, nullptr};
+    float4 *sorted[2] = {nullptr, nullptr}, *sorted_m = nullptr;
+    uint8_t *flags_m = nullptr; int32_t *list_m = nullptr;
     uint2 *cellmap[2] = {nullptr, nullptr};
     int32_t *cell_cnt[2] = {nullptr, nullptr};
     int32_t *g_rank = nullptr, *g_loc = nullptr;
@@ -1035,7 +1038,8 @@ struct EngSlot {
     BSort isortw{nullptr, nullptr};
     BScan iscan{nullptr, nullptr, 0};
     float *ivox = nullptr;                            // [B][S][P][3] voxel-downsampled ICP clouds
-    float4 *isorted[2] = {nullptr, nullptr};
+    float4 *isorted[2] = {nullptr, nullptr}, *isorted_m = nullptr;
+    uint8_t *iflags_m = nullptr; int32_t *ilist_m = nullptr;
     uint2 *icellmap[2] = {nullptr, nullptr};
     int32_t *icell_cnt[2] = {nullptr, nullptr};
     int32_t *ig_rank = nullptr, *ig_loc = nullptr;
@@ -1057,6 +1061,7 @@ struct kp_pipeline {
     int64_t NPr = 0, Pr = 0;          // row strides of the engine's own arrays: S*P and P rounded up to 64 (aligned vector access)
     bool use_graph = true, profiling = false, use_vbi_icp = false, use_vbi_knn = false;
     double rho_mult_a = 1.15, rho_mult_b = 2.0;
+    double knn_mid = 1.5;             // cell of the mid level (x the level-0 cell); 0 = no mid level (KP_KNN_MID)
     int knn_rad = 1;                  // level-0 block radius in cells (KP_KNN_RAD): 1 = 27 cells of the full edge, 2 = 125 cells of half the edge
     std::vector<EngSlot> slots;
     float *d_tab = nullptr;
@@ -1184,9 +1189,11 @@ struct KnnStage {
     VbiArgs vbi_args;
     DOut n_old;                      // points left to the grid level 0 (all of them without an index)
     GridArgs fine, coarse;           // level-0 grid (fallback) and level-1 grid
-    uint8_t *flags0, *flags1; int64_t flag_stride;
-    int32_t *list0, *list1; int64_t list_stride;
-    DOut cnt0, cnt1;
+    bool mid_on;                     // a mid level between them: the level-0 leftovers through the thread-per-query kernel on a
+    GridArgs mid;                    // moderately coarser grid, so that only real outliers reach the warp-per-query level 1
+    uint8_t *flags0, *flags1, *flags_m; int64_t flag_stride;
+    int32_t *list0, *list1, *list_m; int64_t list_stride;
+    DOut cnt0, cnt1, cnt_m;
     DCnt n;
 };
 int stage_knn(kp_pipeline *pl, kp_ctx *ctx, const KnnStage &k, int nseg, int64_t cap_rows, const BScan &sc, DOut sink, bool build_vbi)
@@ -1203,6 +1210,12 @@ int stage_knn(kp_pipeline *pl, kp_ctx *ctx, const KnnStage &k, int nseg, int64_t
     if (k.vbi) KP_TRY(kp_knn_batch_vbi(ctx, *k.batch, cap_rows));
     KP_TRY(kp_knn_batch_level0(ctx, *k.batch, cap_rows));
     KP_TRY(kp_b_compact_index(L, sc, k.n, k.flags0, k.flag_stride, k.list0, k.list_stride, k.cnt0));
+    if (k.mid_on) {
+        KP_TRY(stage_grid(pl, ctx, k.mid, nseg, cap_rows, sc, sink));
+        KP_CUDA(ctx, cudaMemsetAsync(k.flags_m, 0, (size_t)nseg * k.flag_stride, ctx->stream));
+        KP_TRY(kp_knn_batch_mid(ctx, *k.batch, cap_rows));
+        KP_TRY(kp_b_compact_index(L, sc, k.n, k.flags_m, k.flag_stride, k.list_m, k.list_stride, k.cnt_m));
+    }
     KP_TRY(stage_grid(pl, ctx, k.coarse, nseg, cap_rows, sc, sink));
     KP_CUDA(ctx, cudaMemsetAsync(k.flags1, 0, (size_t)nseg * k.flag_stride, ctx->stream));
     KP_TRY(kp_knn_batch_level1(ctx, *k.batch, cap_rows));
@@ -1220,16 +1233,18 @@ GridArgs main_grid_args(kp_pipeline *pl, EngSlot &s, int level, const float *xyz
     const int64_t NPs = pl->NPr;                                 // row stride of every main-branch array
     GridArgs a;
     memset(&a, 0, sizeof a);
-    a.g = &s.dyn->g[level]; a.g_stride = sizeof(EngDyn);
+    // level 2 = the mid grid: its cell map and run starts reuse the level-0 grid's memory (level 0 is done by then; the
+    // level-0 ROWS stay: they are the query points of every later level), its rows have their own array
+    a.g = level == 2 ? &s.dyn->gm[0] : &s.dyn->g[level]; a.g_stride = sizeof(EngDyn);
     a.xyz = xyz; a.xyz_stride = NPs; a.n = n;
     a.b6 = s.dyn->b6; a.b6_stride = sizeof(EngDyn) / 4; a.parent = nullptr; a.parent_mult = 1.0;
-    a.cell = level == 0 ? cell / (double)pl->knn_rad : 3.0 * cell;
-    a.sorted = s.sorted[level]; a.sorted_stride = NPs;
-    a.cellmap = s.cellmap[level]; a.map_stride = pl->cap_cells / 32 + 64;
-    a.cell_cnt = s.cell_cnt[level]; a.cnt_stride = NPs + 64;
+    a.cell = level == 0 ? cell / (double)pl->knn_rad : (level == 2 ? pl->knn_mid * cell : 3.0 * cell);
+    a.sorted = level == 2 ? s.sorted_m : s.sorted[level]; a.sorted_stride = NPs;
+    a.cellmap = s.cellmap[level == 2 ? 0 : level]; a.map_stride = pl->cap_cells / 32 + 64;
+    a.cell_cnt = s.cell_cnt[level == 2 ? 0 : level]; a.cnt_stride = NPs + 64;
     a.rank = s.g_rank; a.loc = s.g_loc; a.tmp_stride = NPs;
     a.cap_cells = pl->cap_cells;
-    a.nocc = DYN_OUT(s, nocc[level]);
+    a.nocc = level == 2 ? DYN_OUT(s, nocc_m[0]) : DYN_OUT(s, nocc[level]);
     return a;
 }
 
@@ -1241,7 +1256,11 @@ int stage_sor(kp_pipeline *pl, EngSlot &s, int use, const float *in, const uint3
     const int B = pl->B;
     const int64_t NPs = pl->NPr;
     KP_PROF(ctx, use == 0 ? "sor" : "floor_sor");
-    const double cell = kp_knn_cell_from_voxel(pl->cfg.voxel_size, k);
+    // level-0 cell: multiples of the radius that holds k points of a one-point-per-voxel surface (swept per search: KP_KNN_MULT_SOR / _FSOR)
+    static const double mult_env[2] = {getenv("KP_KNN_MULT_SOR") ? atof(getenv("KP_KNN_MULT_SOR")) : 0.0, getenv("KP_KNN_MULT_FSOR") ? atof(getenv("KP_KNN_MULT_FSOR")) : 0.0};
+    // (swept on the WFOV frame with the mid level in place: 1.3 for k = 20, 1.1 for k = 50; without a mid level 1.5 / 1.3)
+    const double mult_def = pl->knn_mid > 0.0 ? (k <= 32 ? 1.3 : 1.1) : (k <= 32 ? 1.5 : 1.3);
+    const double cell = pl->cfg.voxel_size * (mult_env[use] > 0.0 ? mult_env[use] : mult_def) * sqrt((double)k / 3.14159265358979);
     KnnStage ks;
     ks.batch = use == 0 ? &s.knn_sor : &s.knn_fsor;
     ks.vbi = pl->use_vbi_knn;
@@ -1258,9 +1277,11 @@ int stage_sor(kp_pipeline *pl, EngSlot &s, int use, const float *in, const uint3
     ks.n_old = DYN_OUT(s, n_old[use]);
     ks.fine = main_grid_args(pl, s, 0, in, ks.vbi ? DYN_CNT(s, n_old[use]) : n, cell);
     ks.coarse = main_grid_args(pl, s, 1, in, n, cell);
-    ks.flags0 = s.flags[0]; ks.flags1 = s.flags[1]; ks.flag_stride = NPs;
-    ks.list0 = s.list[0]; ks.list1 = s.list[1]; ks.list_stride = NPs;
-    ks.cnt0 = DYN_OUT(s, cnt_l0[use]); ks.cnt1 = DYN_OUT(s, cnt_l1[use]);
+    ks.mid_on = pl->knn_mid > 0.0;
+    ks.mid = main_grid_args(pl, s, 2, in, n, cell);
+    ks.flags0 = s.flags[0]; ks.flags1 = s.flags[1]; ks.flags_m = s.flags_m; ks.flag_stride = NPs;
+    ks.list0 = s.list[0]; ks.list1 = s.list[1]; ks.list_m = s.list_m; ks.list_stride = NPs;
+    ks.cnt0 = DYN_OUT(s, cnt_l0[use]); ks.cnt1 = DYN_OUT(s, cnt_l1[use]); ks.cnt_m = DYN_OUT(s, cnt_lm[use]);
     ks.n = n;
     KP_TRY(stage_knn(pl, ctx, ks, B, NPs, s.scan, dout(s.sink, 4), true));
     {
@@ -1387,9 +1408,13 @@ int stage_icp(kp_pipeline *pl, EngSlot &s, kp_ctx *ctx)
     ks.coarse.g = &s.dyn->g[3]; ks.coarse.n = ntgt; ks.coarse.cell = 3.0 * g.cell;
     ks.coarse.sorted = s.isorted[1]; ks.coarse.cellmap = s.icellmap[1]; ks.coarse.cell_cnt = s.icell_cnt[1];
     ks.coarse.nocc = DYN_OUT(s, nocc[3]);
-    ks.flags0 = s.iflags[0]; ks.flags1 = s.iflags[1]; ks.flag_stride = Pr;
-    ks.list0 = s.ilist[0]; ks.list1 = s.ilist[1]; ks.list_stride = Pr;
-    ks.cnt0 = DYN_OUT(s, cnt_l0[2]); ks.cnt1 = DYN_OUT(s, cnt_l1[2]);
+    // (normals are a radius-capped search on a grid whose cell covers the radius: level 0 certifies everything but fp32
+    // ties, so no mid level here)
+    ks.mid_on = false;
+    ks.mid = g;
+    ks.flags0 = s.iflags[0]; ks.flags1 = s.iflags[1]; ks.flags_m = s.iflags_m; ks.flag_stride = Pr;
+    ks.list0 = s.ilist[0]; ks.list1 = s.ilist[1]; ks.list_m = s.ilist_m; ks.list_stride = Pr;
+    ks.cnt0 = DYN_OUT(s, cnt_l0[2]); ks.cnt1 = DYN_OUT(s, cnt_l1[2]); ks.cnt_m = DYN_OUT(s, cnt_lm[2]);
     ks.n = ntgt;
     {
         KP_PROF(ctx, "normals");
@@ -1443,6 +1468,7 @@ int slot_create(kp_pipeline *pl, EngSlot &s)
         SA(s.flags[l], B * NPr); SA(s.list[l], B * NPr);
     }
     SA(s.g_rank, B * NPr); SA(s.g_loc, B * NPr);
+    if (pl->knn_mid > 0.0) { SA(s.sorted_m, B * NPr); SA(s.flags_m, B * NPr); SA(s.list_m, B * NPr); }
     SA(s.mean, B * NPr); SA(s.csum_tmp, B * (NPr / 1024 + NPr / 1048576 + 16));
     SA(s.mask, B * NPr); SA(s.mask2, B * NPr);
     SAZ(s.n_up, B); SAZ(s.sink, B);
@@ -1467,6 +1493,9 @@ int slot_create(kp_pipeline *pl, EngSlot &s)
             e.flags0 = s.flags[0] + (size_t)b * NPr; e.flags1 = s.flags[1] + (size_t)b * NPr;
             e.list0 = s.list[0] + (size_t)b * NPr; e.list1 = s.list[1] + (size_t)b * NPr;
             e.cnt0 = &s.dyn[b].cnt_l0[use]; e.cnt1 = &s.dyn[b].cnt_l1[use];
+            if (pl->knn_mid > 0.0) {
+                e.gm = &s.dyn[b].gm[0]; e.flags_m = s.flags_m + (size_t)b * NPr; e.list_m = s.list_m + (size_t)b * NPr; e.cnt_m = &s.dyn[b].cnt_lm[use];
+            }
             e.mean = s.mean + (size_t)b * NPr;
         }
         // voxel-brick level 0: rho_a certifies the dense parts of the cloud, rho_b the sparse ones (multiples of the radius
@@ -1490,6 +1519,7 @@ int slot_create(kp_pipeline *pl, EngSlot &s)
             SA(s.iflags[l], B * Pr); SA(s.ilist[l], B * Pr);
         }
         SA(s.ig_rank, B * Pr); SA(s.ig_loc, B * Pr);
+        if (pl->knn_mid > 0.0) { SA(s.isorted_m, B * Pr); SA(s.iflags_m, B * Pr); SA(s.ilist_m, B * Pr); }
         SA(s.nrm, B * Pr * 3);
         SA(s.ivijk, (size_t)B * S * Pr); SA(s.ivijk_sorted, B * Pr); SA(s.ibricks, (size_t)B * pl->cap_bricks);
         SAZ(s.isink, (size_t)B * S);
@@ -1717,7 +1747,7 @@ int kp_pipeline_create(int device, const kp_pipeline_cfg *cfg, const float *h_xy
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
     // frames in flight = n_streams: batches of B frames share every launch, W batch slots overlap
     const int fl = cfg->n_streams < 1 ? 1 : (cfg->n_streams > 32 ? 32 : cfg->n_streams);
-    int B = fl < 4 ? fl : 4;
+    int B = fl >= 16 ? 8 : (fl < 4 ? fl : 4);      // (measured: 170-181 frames/s for every B from 1 to 8; larger B = fewer launches per frame)
     if (getenv("KP_PIPE_BATCH")) B = atoi(getenv("KP_PIPE_BATCH"));
     if (B < 1) B = 1;
     if (B > 16) B = 16;
@@ -1730,6 +1760,7 @@ int kp_pipeline_create(int device, const kp_pipeline_cfg *cfg, const float *h_xy
     p->use_vbi_icp = getenv("KP_ICP_VBI") && atoi(getenv("KP_ICP_VBI")) != 0;   // 8 % fewer ICP pass time, paid back by the index build: off unless asked for
     p->use_vbi_knn = getenv("KP_KNN_VBI") && atoi(getenv("KP_KNN_VBI")) != 0;   // measured slower than the grid level 0: off unless asked for
     p->knn_rad = (getenv("KP_KNN_RAD") && atoi(getenv("KP_KNN_RAD")) == 2) ? 2 : 1;
+    if (getenv("KP_KNN_MID")) p->knn_mid = atof(getenv("KP_KNN_MID"));
     if (getenv("KP_VBI_RHO_A")) p->rho_mult_a = atof(getenv("KP_VBI_RHO_A"));
     if (getenv("KP_VBI_RHO_B")) p->rho_mult_b = atof(getenv("KP_VBI_RHO_B"));
     const int S = cfg->S;

@@ -1648,7 +1648,9 @@ int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, 
     if ((size_t)KQ_WARPS * capw * 12 > 96 * 1024) capw = next_pow2(k + 64 > 128 ? k + 64 : 128);
     out->cap_warp = capw;
     if (k > HQ_KMAX) return kp_set_err(ctx, KP_E_ARG, "frame engine: k = %d neighbours exceeds the histogram kernel's %d", k, HQ_KMAX);
-    std::vector<KnnParams> h((size_t)3 * nseg);
+    std::vector<KnnParams> h((size_t)4 * nseg);
+    out->has_mid = nseg > 0 && segs[0].gm != nullptr;
+    out->cap_mid = k + 24;                       // the mid level's bins are wider: more room behind the k-th entry
     for (int s = 0; s < nseg; ++s) {
         const KpKnnSegDesc &d = segs[s];
         KnnParams p;
@@ -1662,10 +1664,14 @@ int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, 
         a.cap = out->cap_hist; a.gdev = d.g0; a.nq_dev = d.n; a.strag_flags = d.flags0;
         a.vbi = d.vbi; a.rho_a = rho_a; a.rho_b = rho_b;
         h[s] = a;
-        // level 1: the level-0 leftovers (list0), one warp each, against the coarse grid
+        // level 1: the leftovers of the level before (list0, or the mid level's list), one warp each, against the coarse grid
         KnnParams b = p;
-        b.cap = out->cap_hist; b.gdev = d.g1; b.qlist = d.list0; b.qcount = d.cnt0; b.strag_flags = d.flags1; b.rad = 1;
+        b.cap = out->cap_hist; b.gdev = d.g1; b.qlist = d.gm ? d.list_m : d.list0; b.qcount = d.gm ? d.cnt_m : d.cnt0; b.strag_flags = d.flags1; b.rad = 1;
         h[(size_t)nseg + s] = b;
+        // mid level: the level-0 leftovers, one THREAD each, histogram select with 64 bins against a moderately coarser grid
+        KnnParams m2 = p;
+        m2.cap = out->cap_mid; m2.gdev = d.gm; m2.qlist = d.list0; m2.qcount = d.cnt0; m2.strag_flags = d.flags_m; m2.rad = 1;
+        h[(size_t)3 * nseg + s] = m2;
         // stragglers: ring expansion on the coarse grid
         KnnParams c = p;
         c.cap = capw; c.gdev = d.g1; c.qlist = d.list1; c.qcount = d.cnt1;
@@ -1679,6 +1685,8 @@ int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, 
     const size_t smem_w = (size_t)KQ_WARPS * capw * (sizeof(double) + sizeof(int));
     if (smem_w > 200 * 1024) return kp_set_err(ctx, KP_E_ARG, "k = %d neighbours is too many for the per-warp buffer", k);
     if (smem_w > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+    const size_t smem_m = (size_t)64 * ((size_t)out->cap_mid * 8 + 64 * 2);
+    if (smem_m > 48 * 1024) KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist_b<64, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
     const size_t smem_h = (size_t)(k <= 32 ? 128 : 64) * ((size_t)out->cap_hist * 8 + (size_t)(k <= 32 ? 32 : 64) * 2);
     if (smem_h > 48 * 1024) {
         if (k <= 32) {
@@ -1702,7 +1710,7 @@ template <int NB, int R, int T>
 static int knn_level0_launch(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows, int per_sm, int level = 0)
 {
     const KnnParams *hp = (const KnnParams *)b.h_params + (size_t)level * b.nseg;
-    const size_t smem = (size_t)T * ((size_t)b.cap_hist * 8 + NB * 2);
+    const size_t smem = (size_t)T * ((size_t)(level == 3 ? b.cap_mid : b.cap_hist) * 8 + NB * 2);
     int64_t gx = (cap_rows + T - 1) / T;
     if (gx > (int64_t)ctx->sm_count * per_sm) gx = (int64_t)ctx->sm_count * per_sm;
     for (int s0 = 0; s0 < b.nseg; s0 += KNN_ARG_SEGS) {
@@ -1743,7 +1751,15 @@ int kp_knn_batch_vbi(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows)
     KP_LAUNCH_CHECK(ctx);
     return KP_OK;
 }
-// level 1: the level-0 leftovers (compacted list), one warp each, best-first on the coarse grid
+// mid level: the level-0 leftovers (compacted list: full warps) through the thread-per-query histogram kernel, 64 bins,
+// on a grid whose cell is ~1.7 x the level-0 cell.  A leftover is typically a point of a sparse part of the cloud whose
+// k-th neighbour lies just outside the level-0 block; the warp-per-query level 1 costs ~20 x a level-0 query, this ~3 x.
+int kp_knn_batch_mid(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows)
+{
+    KP_PROFB(ctx, "knn_mid", 0.0);
+    return knn_level0_launch<64, 1, 64>(ctx, b, cap_rows / 4 + 1, 8, 3);
+}
+// level 1: the leftovers of the level before (compacted list), one warp each, best-first on the coarse grid
 int kp_knn_batch_level1(kp_ctx *ctx, const KpKnnBatch &b, int64_t cap_rows)
 {
     KP_PROFB(ctx, "knn_level1", 0.0);
