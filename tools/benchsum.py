@@ -1,5 +1,6 @@
 import sys, json
-for ln in sys.stdin:
+src = open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin
+for ln in src:
     ln = ln.strip()
     if not ln.startswith("{"):
         continue
