@@ -159,7 +159,7 @@ def cpu_baseline(cfg, depth, tab, T_fuse, T_icp, frames):
 # kernel family of the profile -> (dominant kernel, binding resource)
 LEAF = {
     "knn_level0": ("k_knn_hist_b", "issue"), "knn_level1": ("k_knn_wbf_b", "issue"), "knn_stragglers": ("k_knn_b", "issue"),
-    "knn_vbi": ("k_knn_vbi_b", "issue"), "knn_mid": ("k_knn_hist_b", "issue"), "icp": ("k_icp_iter_b", "issue"),
+    "knn_vbi": ("k_knn_vbi_b", "issue"), "knn_mid": ("k_knn_mid_b", "issue"), "icp": ("k_icp_iter_b", "issue"),
     "radix_sort": ("k_rs_scatter", "hbm"), "ransac_score": ("k_e_ransac_score", "fp64"), "ransac_fit": ("k_e_ransac_fit", "latency"),
     "ransac_select": ("k_e_ransac_select", "latency"),
     "unproject_transform": ("k_unproject", "hbm"), "voxel_mean": ("k_e_voxel_mean", "hbm"), "voxel_keys": ("k_e_voxel_keys", "hbm"),
@@ -169,7 +169,7 @@ LEAF = {
 }
 
 
-def family_bytes(st, cfg, S, P):
+def family_bytes(st, cfg, S, P, icp_iters=()):
     """Algorithmic HBM bytes per FRAME of every streaming family, from the frame's own counts.
     N = fused rows, Nv = valid, M = voxels, K = kept by SOR, lo = band, E = merged, per ICP cloud P rows."""
     NP = S * P
@@ -193,7 +193,11 @@ def family_bytes(st, cfg, S, P):
     b["merge"] = (K - lo) * 24
     b["ransac_score"] = lo * 12 + cfg.ransac_iters * 40
     b["knn_level0"] = (M + E + icp * Mi[0]) * 16 + (M + E) * 8 + icp * Mi[0] * 12
-    b["icp"] = 0.0
+    # level-0 leftovers of the two SOR searches through the mid level: the query row + its output
+    b["knn_mid"] = sum(st["leftovers_l0"][:2]) * (16 + 8)
+    # a pass reads and rewrites the moving source (2 x 24 B) and its partner index (2 x 4 B), and gathers the partner's
+    # row (16 B) and normal (12 B); pair i runs icp_iters[i] + 1 working passes over the points of sub cloud i + 1
+    b["icp"] = float(sum((int(it) + 1) * 84 * Mi[i + 1] for i, it in enumerate(icp_iters))) if icp else 0.0
     return b
 
 
@@ -456,7 +460,7 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         fam = dict(prof)
-        algo = family_bytes(stats, cfg, S, P) if stats else {}
+        algo = family_bytes(stats, cfg, S, P, [int(x) for x in last[0].icp_iters[:S - 1]]) if stats else {}
         leaf_ms = sum(v["ms"] for k, v in fam.items() if k in LEAF) or 1.0
         table = {}
         for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
@@ -472,22 +476,35 @@ def main():
             t = table[top]
             ncu = {}
             try:
-                ncu = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json"))).get(t["kernel"], {})
+                # every captured instance of the kernel (template arguments differ per k), weighted by its launches
+                allk = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json")))
+                inst = [v for k_, v in allk.items() if k_ == t["kernel"] or k_.startswith(t["kernel"] + "<")]
+                nl = sum(v["launches"] for v in inst)
+                if nl:
+                    wavg = lambda key: sum(v[key] * v["launches"] for v in inst) / nl
+                    ncu = {"dram_bytes_per_launch": round(wavg("dram_bytes_per_launch")), "issue_active_frac": round(wavg("issue_active_frac"), 4),
+                           "warp_instructions_per_launch": round(wavg("warp_instructions_per_launch")),
+                           "lanes_per_instruction": round(wavg("lanes_per_instruction"), 2), "source": inst[0]["source"],
+                           "frames_per_launch": inst[0].get("frames_per_launch")}
             except Exception:
                 pass
-            launches_per_frame = {"knn_level0": 3.0, "icp": 1.0}.get(top, 1.0)
+            # working launches per batch: three level-0 searches (SOR, floor SOR, normals); an ICP pass launch advances every pair
+            # of the batch, and the pairs need icp_iters + 1 of the max_iter + 1 enqueued passes (the others leave at once)
+            launches_per_batch = {"knn_level0": 3.0}.get(top, 1.0)
             if top == "icp":
-                launches_per_frame = float(np.mean([int(last[0].icp_iters[i]) + 1 for i in range(2)]))
+                launches_per_batch = float(np.mean([int(last[0].icp_iters[i]) + 1 for i in range(S - 1)]))
             ach = t["algorithmic_GBps"]
             roofline = {"kernel": t["kernel"], "family": top, "bound": t["bound"], "achieved": ach, "peak": peak, "unit": "GB/s",
                         "frac": round(ach / peak, 5), "traffic": ncu.get("dram_bytes_per_launch"), "traffic_source": ncu.get("source"),
-                        "peak_source": peak_src, "avg_launch_ms": round(t["ms_per_frame"] / launches_per_frame, 4),
-                        "algorithmic_bytes_per_launch": round(algo.get(top, 0.0) / launches_per_frame),
+                        "traffic_frames_per_launch": ncu.get("frames_per_launch"),
+                        "peak_source": peak_src, "frames_per_launch": fpl, "avg_launch_ms": round(t["ms_per_frame"] * fpl / launches_per_batch, 4),
+                        "algorithmic_bytes_per_launch": round(algo.get(top, 0.0) * fpl / launches_per_batch),
                         "issue_active_frac": ncu.get("issue_active_frac"), "warp_instructions_per_launch": ncu.get("warp_instructions_per_launch"),
-                        "note": "dominant kernel by summed device time (CUDA events around every kernel family, one batch in flight). "
-                                "It is bound by instruction issue, not by HBM: `achieved` / `frac` are its compulsory bytes over its run time against the "
-                                "HBM peak, as the contract asks; `issue_active_frac` (ncu, profiles/) is the fraction of its real ceiling. "
-                                "HBM-bound families and their fractions are in `kernels`."}
+                        "lanes_per_instruction": ncu.get("lanes_per_instruction"),
+                        "note": "dominant kernel by summed device time (CUDA events around every kernel family, one batch in flight); a launch "
+                                "covers `frames_per_launch` frames. It is bound by instruction issue, not by HBM: `achieved` / `frac` are its "
+                                "compulsory bytes over its run time against the HBM peak, as the contract asks; `issue_active_frac` and "
+                                "`lanes_per_instruction` (ncu, profiles/) describe its real ceiling. HBM-bound families and their fractions are in `kernels`."}
         cb = None
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(cfg, depth, tab, T_fuse, T_icp, args.cpu_sample_frames)

@@ -431,8 +431,10 @@ class TransformationEstimationPointToPoint:
         ``manual_pointcloud_registration.py:90-92``: Umeyama / Kabsch over a handful of hand-picked pairs
         (host-side; three to a dozen points are not device work)."""
         c = np.asarray(corres).astype(np.int64).reshape(-1, 2)
-        s = source._p.peek_host()[c[:, 0]]          # (read-only: the device copies stay valid)
-        t = target._p.peek_host()[c[:, 1]]
+        # read-only view of our own clouds (their device copies stay valid); anything else with a `.points` array works too
+        rows = lambda pc: pc._p.peek_host() if isinstance(pc, PointCloud) else np.asarray(pc.points)
+        s = rows(source)[c[:, 0]]
+        t = rows(target)[c[:, 1]]
         T = np.eye(4)
         if len(c) == 0:
             return T

@@ -20,6 +20,7 @@ def num(r, idx, key):
         return None
 
 def main(paths, out_path):
+    fpl = int(os.environ.get("NCU_FRAMES_PER_LAUNCH", "0")) or None     # frames per launch of the captured command
     acc = {}
     for p in paths:
         for idx, units, r in rows_of(p):
@@ -29,7 +30,7 @@ def main(paths, out_path):
             short = (m.group(1) + (m.group(2) or "")) if m else name[:40]
             bscale = lambda k: {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[idx[k]], 1.0)
             tscale = {"nsecond": 1e-6, "ns": 1e-6, "usecond": 1e-3, "us": 1e-3, "msecond": 1.0, "ms": 1.0, "second": 1e3, "s": 1e3}.get(units[idx["gpu__time_duration.sum"]], 1e-6)
-            e = acc.setdefault(short, {"launches": 0, "dram": 0.0, "inst": 0.0, "issue": 0.0, "occ": 0.0, "lanes": 0.0, "ms": 0.0, "regs": 0, "names": set()})
+            e = acc.setdefault(short, {"launches": 0, "dram": 0.0, "inst": 0.0, "issue": 0.0, "occ": 0.0, "lanes": 0.0, "ms": 0.0, "regs": 0, "names": set(), "each": []})
             e["launches"] += 1
             e["dram"] += (num(r, idx, "dram__bytes_read.sum") or 0) * bscale("dram__bytes_read.sum") + (num(r, idx, "dram__bytes_write.sum") or 0) * bscale("dram__bytes_write.sum")
             e["inst"] += num(r, idx, "smsp__inst_executed.sum") or 0
@@ -39,17 +40,19 @@ def main(paths, out_path):
             e["ms"] += (num(r, idx, "gpu__time_duration.sum") or 0) * tscale
             e["regs"] = int(num(r, idx, "launch__registers_per_thread") or 0)
             e["names"].add(name[:90])
+            e["each"].append({"ms": round((num(r, idx, "gpu__time_duration.sum") or 0) * tscale, 4), "warp_instructions": int(num(r, idx, "smsp__inst_executed.sum") or 0),
+                              "grid": r[idx["Grid Size"]] if "Grid Size" in idx else None})
     res = {}
     for k, e in acc.items():
         n = e["launches"]
         res[k] = {"launches": n, "dram_bytes_per_launch": round(e["dram"] / n), "warp_instructions_per_launch": round(e["inst"] / n),
                   "issue_active_frac": round(e["issue"] / n / 100.0, 4), "occupancy_frac": round(e["occ"] / n / 100.0, 4),
-                  "lanes_per_instruction": round(e["lanes"] / n, 2), "ncu_ms_per_launch": round(e["ms"] / n, 4), "registers": e["regs"],
+                  "lanes_per_instruction": round(e["lanes"] / n, 2), "ncu_ms_per_launch": round(e["ms"] / n, 4), "registers": e["regs"], "frames_per_launch": fpl, "per_launch": e["each"],
                   "source": "profiles/ (ncu --set full --clock-control none, %s; cold-cache, serialised: shares, not absolutes)" % ", ".join(os.path.basename(p) for p in paths),
                   "instances": sorted(e["names"])}
     json.dump(res, open(out_path, "w"), indent=1)
     for k, v in res.items():
-        print(k, {a: b for a, b in v.items() if a not in ("source", "instances")})
+        print(k, {a: b for a, b in v.items() if a not in ("source", "instances", "per_launch")})
 
 if __name__ == "__main__":
     main(sys.argv[2:], sys.argv[1])
