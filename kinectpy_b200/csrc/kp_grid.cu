@@ -701,6 +701,9 @@ __global__ void __launch_bounds__(KQ_WARPS * 32) k_knn_b(const KnnParams *pp)
 // binning only: a bin index is a monotone function of the fp32 distance, whose relative error (< 6e-7)
 // is covered by the 1e-6 margins of the certificate, so the result is the exact double-precision answer
 // or the query is handed to the next level (flag), never an approximation.
+#ifndef HQ_ROLL
+#define HQ_ROLL 1
+#endif
 constexpr int HQ_THREADS = 128;
 constexpr int HQ_KMAX = 64;
 constexpr float HQ_MAGIC = 8388608.0f;          // 2^23: adding it leaves round(x) in the low mantissa bits
@@ -886,25 +889,40 @@ __device__ __forceinline__ void hq_query(const KnnParams &p, const KpGridDev &g,
     bool bounded = false;                       // pass 1 stopped visiting cells beyond a bound found on the way
     bool all;
     if constexpr (R == 1) {
-        // 27 cells = 9 columns: ranges stay in registers for pass 2
+        // 27 cells = 9 columns.  The nine cell-map lookups are unrolled and requested together, ahead of the first run's
+        // candidates; the two candidate loops are NOT unrolled over the columns (HQ_ROLL): nine copies of each made the
+        // kernel 107 KB of SASS against a 32 KB L1.5 / 6 KB L0 instruction cache, and with every warp of an SM at a
+        // different place in it a quarter of the stall samples were instruction fetches (ncu: stall_no_inst).  The ranges
+        // then live in local memory (18 words per thread, L1 hits): one load per column of 10-40 candidates.
         int2 rng[9];
-        const int order[9] = {4, 1, 3, 5, 7, 0, 2, 6, 8};
+        float gap2[9];
         const float fb = hq_budget(budget);
-        // the nine cell-map lookups are requested together, ahead of the first run's candidates
 #pragma unroll
-        for (int ci = 0; ci < 9; ++ci) rng[ci] = hq_column(g, G, order[ci] / 3 - 1, order[ci] % 3 - 1, 1, fb);
+        for (int ci = 0; ci < 9; ++ci) {
+            constexpr int order[9] = {4, 1, 3, 5, 7, 0, 2, 6, 8};
+            const int dx = order[ci] / 3 - 1, dy = order[ci] % 3 - 1;
+            rng[ci] = hq_column(g, G, dx, dy, 1, fb);
+            const float gx = hq_gap(G, 0, dx), gy = hq_gap(G, 1, dy);
+            gap2[ci] = gx * gx + gy * gy;
+        }
+#if HQ_ROLL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int ci = 0; ci < 9; ++ci) count(rng[ci]);
         select_bin();
         all = b < 0;                            // fewer than k in range: the loop ran over every bin, take them all
         if (b < 0) b = NB - 1;
         if (m > p.cap || (m < k && !G.cap_binding)) { p.strag_flags[q] = 1; return; }
         const float fb2 = hq_budget(fmin(budget, ((double)b + 1.0) / (double)G.scale));
+#if HQ_ROLL
+#pragma unroll 1
+#else
 #pragma unroll
-        for (int ci = 0; ci < 9; ++ci) {
-            const float gx = hq_gap(G, 0, order[ci] / 3 - 1), gy = hq_gap(G, 1, order[ci] % 3 - 1);
-            if (gx * gx + gy * gy <= fb2) collect(rng[ci]);
-        }
+#endif
+        for (int ci = 0; ci < 9; ++ci)
+            if (gap2[ci] <= fb2) collect(rng[ci]);
     } else {
         // 125 cells = 25 columns.  Phase A = the 9 inner columns; its histogram bounds the k-th distance, and
         // phase B (the outer ring) only visits the cells that reach inside that bound.
