@@ -133,7 +133,13 @@ class ClockSampler:
 def make_inputs(mode_name, distinct, rank, scale=1e-3, sensors=3):
     from kinectpy_b200 import synth
     mode = synth.MODES[mode_name]
-    depth, tab, T = synth.render_sequence(mode, distinct, sensors, first_frame=rank * distinct)
+    # Weak scaling: the per-GPU work is the same on every rank -- the same `distinct` frames, their order rotated by rank
+    # (what round-robin sharding of a long recording gives every rank statistically).  Round 2 first gave rank r the
+    # window [r * distinct, (r + 1) * distinct) of the synthetic sequence: those windows differ by up to 11 % in cost
+    # (the figure moves through the room), which read as 0.91 scaling efficiency at 4 and 8 GPUs although every GPU,
+    # alone on its window-0 data, ran the same 176 ms (profiles/r02_g_gpu_variance.json).
+    depth, tab, T = synth.render_sequence(mode, distinct, sensors, first_frame=0)
+    depth = np.roll(depth, -(rank % max(distinct, 1)), axis=0)
     T_fuse = synth.scale_extrinsics(T, scale)
     T_icp = np.stack([synth.perturbed_extrinsic(T_fuse[s], ICP_START["angle_deg"], tuple(ICP_START["shift_mm"]), unit_scale=scale) if s else T_fuse[s]
                       for s in range(sensors)])
@@ -232,7 +238,7 @@ def main():
                 "floor removal (band 20cm, RANSAC 1cm x1000, SOR(50,0.30)) -> p2plane ICP x2 (max_corr 2cm, <=30 it)" % args.mode)
     config = {"workload": workload, "mode": args.mode, "sensors": 3, "frames_per_step_per_gpu": args.frames_per_step,
               "distinct_frames": args.distinct_frames, "frames_in_flight_per_gpu": args.streams, "host_threads_per_gpu": 1,
-              "host_cores": cores, "sharding": "frames round-robin over ranks, no collective",
+              "host_cores": cores, "sharding": "frames are independent units, no collective; every rank runs the same distinct frames (order rotated by rank): per-GPU work fixed",
               "icp_start": "ground-truth extrinsic perturbed by %.1f deg about (1,1,1)/sqrt(3) and (%+d,%+d,%+d) mm" %
                            (ICP_START["angle_deg"], *ICP_START["shift_mm"]),
               "sensor_yaw_deg": SENSOR_YAW_DEG,
@@ -340,8 +346,17 @@ def main():
         lib.kp_host_free(hout)
 
     # ------------------------------------------------------------------ reduce over ranks (max time) before the rank-0-only legs
+    per_rank = None
     if world > 1:
-        t = torch.tensor([ms, e2e["ms"] if e2e else 0.0], dtype=torch.float64, device="cuda")
+        # every rank's own figures travel to rank 0 (after the timed regions): the spread tells a slow GPU from a busy host
+        mine = torch.tensor([ms, e2e["ms"] if e2e else 0.0, clocks.get("sm_mhz") or 0.0, 1.0 if "sw_power_cap" in clocks.get("reasons", []) else 0.0],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(float(a[0]) / args.steps, 2) for a in allr],
+                    "e2e_ms_per_step": [round(float(a[1]) / args.steps, 2) for a in allr],
+                    "sm_mhz": [float(a[2]) for a in allr], "sw_power_cap": [bool(a[3] > 0) for a in allr]}
+        t = mine[:2].clone()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e_max = float(t[0]), float(t[1])
     else:
@@ -518,6 +533,7 @@ def main():
             "e2e": None if e2e is None else {"value": frames_total / (ms_e2e_max * 1e-3), "unit": UNIT,
                                              "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                                              "ms_per_step": ms_e2e_max / args.steps},
+            "per_rank": per_rank,
             "roofline": roofline, "kernels": table,
             "kernels_note": "per-family device time with %d frames per launch (as in the timed region) and ONE batch in flight, CUDA events around "
                             "every family (serial ms/frame %.3f); the timed region overlaps %d such batches" % (fpl, ms_serial / prof_frames, slots),
