@@ -1729,6 +1729,12 @@ int kp_knn_batch_create(kp_ctx *ctx, const KpKnnSegDesc *segs, int nseg, int k, 
             KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_vbi_b<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
         }
     }
+    // shared memory / L1 split of the level-0 kernels (percent of the maximum shared memory; unset = the driver's choice)
+    if (getenv("KP_KNN_CARVEOUT")) {
+        const int pct = atoi(getenv("KP_KNN_CARVEOUT"));
+        KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist_b<32, 1, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        KP_CUDA(ctx, cudaFuncSetAttribute(k_knn_hist_b<64, 1, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     return KP_OK;
 }
 void kp_knn_batch_destroy(KpKnnBatch *b)
