@@ -48,7 +48,7 @@ def main(paths, out_path):
         res[k] = {"launches": n, "dram_bytes_per_launch": round(e["dram"] / n), "warp_instructions_per_launch": round(e["inst"] / n),
                   "issue_active_frac": round(e["issue"] / n / 100.0, 4), "occupancy_frac": round(e["occ"] / n / 100.0, 4),
                   "lanes_per_instruction": round(e["lanes"] / n, 2), "ncu_ms_per_launch": round(e["ms"] / n, 4), "registers": e["regs"], "frames_per_launch": fpl, "per_launch": e["each"],
-                  "source": "profiles/ (ncu --set full --clock-control none, %s; cold-cache, serialised: shares, not absolutes)" % ", ".join(os.path.basename(p) for p in paths),
+                  "source": "ncu --set full --clock-control none, raw pages %s (cold-cache, serialised: shares, not absolutes)" % ", ".join(paths),
                   "instances": sorted(e["names"])}
     json.dump(res, open(out_path, "w"), indent=1)
     for k, v in res.items():
