@@ -32,7 +32,7 @@ def transform_filtered_image_to_pointcloud(filtered_img, depth_img, gate: float 
     d_rgb, d_xyz = ctx.to_device(rgb), ctx.to_device(xyz16)
     keep = ctx.empty((n,), np.uint8)
     ctx.check(ctx.lib.kp_crop_mask(ctx.handle, d_rgb.ptr, d_xyz.ptr, n, float(gate), keep.ptr, None))
-    return rgbd_to_pointcloud(rgb, xyz16, keep_mask=keep.to_host(), transform=transform)
+    return rgbd_to_pointcloud(rgb, xyz16, transform=transform, _on_device=(d_xyz, keep))
 
 
 def fuse_registered(clouds: Sequence[PointCloud], transforms: Sequence[np.ndarray]) -> PointCloud:

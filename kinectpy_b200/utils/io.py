@@ -40,11 +40,13 @@ def save_depth(depth_fp: str, xyz16: np.ndarray) -> None:
     np.ascontiguousarray(xyz16, dtype=np.int16).reshape(-1, 3).tofile(depth_fp)
 
 
-def rgbd_to_pointcloud(color_img, depth_img, keep_mask=None, transform=None) -> PointCloud:
+def rgbd_to_pointcloud(color_img, depth_img, keep_mask=None, transform=None, _on_device=None) -> PointCloud:
     """int16 XYZ (+ RGB) -> cloud of the valid pixels, in pixel order (``utils/io.py:23-43``).
 
     ``keep_mask`` (uint8 per pixel) and ``transform`` (4x4) are extensions used by the crop / fusion
     callers so that the mask, the extrinsic and the compaction stay in one pass on the device.
+    ``_on_device`` = ``(d_xyz16, d_keep)``: the crop caller's own device copies of ``depth_img`` and of the mask it just
+    computed there (no trip of the mask to the host and back, no second upload of the frame).
     """
     raw = np.asarray(depth_img).reshape(-1, 3)
     if raw.dtype != np.int16:
@@ -59,9 +61,12 @@ def rgbd_to_pointcloud(color_img, depth_img, keep_mask=None, transform=None) -> 
     if n == 0:
         return PointCloud()
     ctx = _cabi.default_context()
-    d16 = ctx.to_device(xyz16)
+    if _on_device is not None:
+        d16, d_keep = _on_device
+    else:
+        d16 = ctx.to_device(xyz16)
+        d_keep = ctx.to_device(np.ascontiguousarray(keep_mask, dtype=np.uint8).reshape(-1)) if keep_mask is not None else None
     pts = ctx.empty((n, 3), np.float32)
-    d_keep = ctx.to_device(np.ascontiguousarray(keep_mask, dtype=np.uint8).reshape(-1)) if keep_mask is not None else None
     t16 = _cabi.T16(transform) if transform is not None else None
     ctx.check(ctx.lib.kp_points_from_xyz16(ctx.handle, d16.ptr, n, t16.ctypes.data if t16 is not None else None,
                                            _cabi.UNPROJECT_DROP_ANY_ZERO, 1.0, d_keep.ptr if d_keep is not None else None,
