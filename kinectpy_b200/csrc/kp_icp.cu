@@ -505,8 +505,11 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_CTAS) k_icp_iter(const __
 {
     icp_iter_body<MODE>(p);
 }
+#ifndef ICP_B_CTAS
+#define ICP_B_CTAS 3   // resident CTAs per SM the batched pass is compiled for (measured: 2 -> 2.71, 3 -> 2.15, 4 -> 2.02 ms alone but no gain for the frame)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_iter_b(const IcpParams *pp)
+__global__ void __launch_bounds__(ICP_THREADS, ICP_B_CTAS) k_icp_iter_b(const IcpParams *pp)
 {
     // CTAs beyond the pair's source count, and every CTA of a converged pair, leave before touching anything else
     const IcpParams *me = pp + blockIdx.y;
