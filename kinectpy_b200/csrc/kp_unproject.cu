@@ -224,15 +224,14 @@ __global__ void __launch_bounds__(UP_THREADS, RAW ? 2 : 3) k_unproject(const __g
             // the slots of a frame afterwards.  No CTA barrier and no atomics inside the frame loop (thousands of
             // warps hitting the frame's 7 words with atomics cost more than the whole unprojection).
             int enc[7] = {kp_f2ord(mn[0]), kp_f2ord(mn[1]), kp_f2ord(mn[2]), kp_f2ord(mx[0]), kp_f2ord(mx[1]), kp_f2ord(mx[2]), cnt};
+            // (order-preserving integer images of the floats: one warp-reduce instruction per number instead of five
+            // shuffle + min steps)
 #pragma unroll
-            for (int sft = 16; sft >= 1; sft >>= 1) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    enc[c] = min(enc[c], __shfl_xor_sync(KP_FULL, enc[c], sft));
-                    enc[3 + c] = max(enc[3 + c], __shfl_xor_sync(KP_FULL, enc[3 + c], sft));
-                }
-                enc[6] += __shfl_xor_sync(KP_FULL, enc[6], sft);
+            for (int c = 0; c < 3; ++c) {
+                enc[c] = __reduce_min_sync(KP_FULL, enc[c]);
+                enc[3 + c] = __reduce_max_sync(KP_FULL, enc[3 + c]);
             }
+            enc[6] = __reduce_add_sync(KP_FULL, enc[6]);
             constexpr int NSETS = RAW ? 2 : 1;
             if (lane == 0) {
                 int4 *slot = reinterpret_cast<int4 *>(p.bounds_enc) +
@@ -245,12 +244,9 @@ __global__ void __launch_bounds__(UP_THREADS, RAW ? 2 : 3) k_unproject(const __g
                 int renc[6] = {kp_f2ord(s ? rmn[0] : mn[0]), kp_f2ord(s ? rmn[1] : mn[1]), kp_f2ord(s ? rmn[2] : mn[2]),
                                kp_f2ord(s ? rmx[0] : mx[0]), kp_f2ord(s ? rmx[1] : mx[1]), kp_f2ord(s ? rmx[2] : mx[2])};
 #pragma unroll
-                for (int sft = 16; sft >= 1; sft >>= 1) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        renc[c] = min(renc[c], __shfl_xor_sync(KP_FULL, renc[c], sft));
-                        renc[3 + c] = max(renc[3 + c], __shfl_xor_sync(KP_FULL, renc[3 + c], sft));
-                    }
+                for (int c = 0; c < 3; ++c) {
+                    renc[c] = __reduce_min_sync(KP_FULL, renc[c]);
+                    renc[3 + c] = __reduce_max_sync(KP_FULL, renc[3 + c]);
                 }
                 if (lane == 0) {
                     int4 *slot = reinterpret_cast<int4 *>(p.bounds_enc) +
