@@ -136,38 +136,51 @@ __device__ __forceinline__ const KpVoxDev &vox_of(const KpVoxDev *vp, int64_t st
 {
     return *reinterpret_cast<const KpVoxDev *>(reinterpret_cast<const char *>(vp) + seg * stride_bytes);
 }
+__device__ __forceinline__ uint32_t vox_key(const KpVoxDev &vp, float x, float y, float z)
+{
+    if (!vp.ok || isnan(x)) return vp.sentinel;
+    const long long ix = (long long)floor(__ddiv_rn(__dsub_rn((double)x, vp.minb[0]), vp.voxel));
+    const long long iy = (long long)floor(__ddiv_rn(__dsub_rn((double)y, vp.minb[1]), vp.voxel));
+    const long long iz = (long long)floor(__ddiv_rn(__dsub_rn((double)z, vp.minb[2]), vp.voxel));
+    return (uint32_t)(((unsigned long long)ix << vp.sh_x) | ((unsigned long long)iy << vp.sh_y) | (unsigned long long)iz);
+}
 __global__ void __launch_bounds__(256) k_e_voxel_keys(const __grid_constant__ VoxArgs a)
 {
     const int seg = blockIdx.y;
     const KpVoxDev vp = vox_of(a.vp, a.vp_stride, seg);
     const float *xyz = a.xyz + 3 * seg * a.xyz_stride;
     uint32_t *keys = a.keys + seg * a.key_stride;
-    // four rows per thread and trip, all twelve loads issued before the first division: the kernel is a stream of
-    // 12-byte rows in and 4-byte keys out, and the three IEEE double divisions per row are latency, not throughput
-    constexpr int U = 4;
+    // A thread owns FOUR CONSECUTIVE rows = 48 bytes = three 16-byte loads, and writes their keys as one 16-byte store; two
+    // such groups per trip, all six loads issued before the first division.  (Segment strides are multiples of 64 rows and
+    // the arenas 256-byte aligned, so every group is 16-byte aligned.)  The kernel is a stream of 12-byte rows in and 4-byte
+    // keys out: the three IEEE double divisions per row are latency, not throughput.
+    constexpr int U = 2;
+    const int64_t groups = a.n / 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < a.n; i0 += U * stride) {
-        float x[U], y[U], z[U];
+    const float4 *x4 = reinterpret_cast<const float4 *>(xyz);
+    uint4 *k4 = reinterpret_cast<uint4 *>(keys);
+    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < groups; g0 += U * stride) {
+        float4 v[U][3];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t i = i0 + u * stride;
-            x[u] = NAN; y[u] = 0.f; z[u] = 0.f;
-            if (i < a.n) { x[u] = xyz[3 * i]; y[u] = xyz[3 * i + 1]; z[u] = xyz[3 * i + 2]; }
+            const int64_t g = g0 + u * stride;
+            if (g < groups) { v[u][0] = x4[3 * g]; v[u][1] = x4[3 * g + 1]; v[u][2] = x4[3 * g + 2]; }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t i = i0 + u * stride;
-            if (i >= a.n) break;
-            uint32_t key = vp.sentinel;
-            if (vp.ok && !isnan(x[u])) {
-                const long long ix = (long long)floor(__ddiv_rn(__dsub_rn((double)x[u], vp.minb[0]), vp.voxel));
-                const long long iy = (long long)floor(__ddiv_rn(__dsub_rn((double)y[u], vp.minb[1]), vp.voxel));
-                const long long iz = (long long)floor(__ddiv_rn(__dsub_rn((double)z[u], vp.minb[2]), vp.voxel));
-                key = (uint32_t)(((unsigned long long)ix << vp.sh_x) | ((unsigned long long)iy << vp.sh_y) | (unsigned long long)iz);
-            }
-            keys[i] = key;
+            const int64_t g = g0 + u * stride;
+            if (g >= groups) break;
+            uint4 k;
+            k.x = vox_key(vp, v[u][0].x, v[u][0].y, v[u][0].z);
+            k.y = vox_key(vp, v[u][0].w, v[u][1].x, v[u][1].y);
+            k.z = vox_key(vp, v[u][1].z, v[u][1].w, v[u][2].x);
+            k.w = vox_key(vp, v[u][2].y, v[u][2].z, v[u][2].w);
+            k4[g] = k;
         }
     }
+    // rows beyond the last full group (n not a multiple of 4)
+    if (blockIdx.x == 0)
+        for (int64_t i = groups * 4 + threadIdx.x; i < a.n; i += blockDim.x) keys[i] = vox_key(vp, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
 }
 // one thread per voxel run: sums its points in input order (the sort is stable) in double, one division, one rounding
 struct VoxMeanArgs {
