@@ -312,6 +312,19 @@ __global__ void __launch_bounds__(256) k_eg_clear(const __grid_constant__ GridAr
     for (long long w = t0; w < words; w += stride) map[w] = make_uint2(0xffffffffu, 0u);
     for (long long i = t0; i <= n; i += stride) cnt[i] = 0;
 }
+__device__ __forceinline__ int eg_cell_of(const KpGridDev &g, float x, float y, float z)
+{
+    const int cx = min(max(kp_cell_coord(g, (double)x, 0), 0), g.dim[0] - 1);
+    const int cy = min(max(kp_cell_coord(g, (double)y, 1), 0), g.dim[1] - 1);
+    const int cz = min(max(kp_cell_coord(g, (double)z, 2), 0), g.dim[2] - 1);
+    return (cx * g.dim[1] + cy) * g.dim[2] + cz;
+}
+__device__ __forceinline__ void eg_mark_cell(uint2 *map, int cell)
+{
+    const unsigned bit = 1u << (cell & 31);
+    // (neighbouring points share cells: skip the atomic when the bit is already visible as set)
+    if (map[cell >> 5].x & bit) atomicAnd(&map[cell >> 5].x, ~bit);
+}
 __global__ void __launch_bounds__(256) k_eg_mark(const __grid_constant__ GridArgs a)
 {
     const int seg = blockIdx.y;
@@ -320,17 +333,30 @@ __global__ void __launch_bounds__(256) k_eg_mark(const __grid_constant__ GridArg
     const float *xyz = a.xyz + 3 * seg * a.xyz_stride;
     uint2 *map = a.cellmap + seg * a.map_stride;
     int32_t *cellidx = a.rank + seg * a.tmp_stride;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float x = xyz[3 * (int64_t)i], y = xyz[3 * (int64_t)i + 1], z = xyz[3 * (int64_t)i + 2];
-        const int cx = min(max(kp_cell_coord(g, (double)x, 0), 0), g.dim[0] - 1);
-        const int cy = min(max(kp_cell_coord(g, (double)y, 1), 0), g.dim[1] - 1);
-        const int cz = min(max(kp_cell_coord(g, (double)z, 2), 0), g.dim[2] - 1);
-        const int cell = (cx * g.dim[1] + cy) * g.dim[2] + cz;
-        cellidx[i] = cell;
-        const unsigned bit = 1u << (cell & 31);
-        // (neighbouring points share cells: skip the atomic when the bit is already visible as set)
-        if (map[cell >> 5].x & bit) atomicAnd(&map[cell >> 5].x, ~bit);
+    // four consecutive rows per thread: three 16-byte loads in, one 16-byte store of the cell indices out (segment strides
+    // are multiples of 64 rows: every group is 16-byte aligned)
+    const int groups = n / 4;
+    const float4 *x4 = reinterpret_cast<const float4 *>(xyz);
+    int4 *c4 = reinterpret_cast<int4 *>(cellidx);
+    for (int gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += gridDim.x * blockDim.x) {
+        const float4 v0 = x4[3 * (int64_t)gidx], v1 = x4[3 * (int64_t)gidx + 1], v2 = x4[3 * (int64_t)gidx + 2];
+        int4 c;
+        c.x = eg_cell_of(g, v0.x, v0.y, v0.z);
+        c.y = eg_cell_of(g, v0.w, v1.x, v1.y);
+        c.z = eg_cell_of(g, v1.z, v1.w, v2.x);
+        c.w = eg_cell_of(g, v2.y, v2.z, v2.w);
+        c4[gidx] = c;
+        eg_mark_cell(map, c.x);
+        if (c.y != c.x) eg_mark_cell(map, c.y);
+        if (c.z != c.y) eg_mark_cell(map, c.z);
+        if (c.w != c.z) eg_mark_cell(map, c.w);
     }
+    if (blockIdx.x == 0)
+        for (int i = groups * 4 + threadIdx.x; i < n; i += blockDim.x) {
+            const int cell = eg_cell_of(g, xyz[3 * (int64_t)i], xyz[3 * (int64_t)i + 1], xyz[3 * (int64_t)i + 2]);
+            cellidx[i] = cell;
+            eg_mark_cell(map, cell);
+        }
 }
 // ranks: exclusive scan of the words' popcounts into .y (tile sums, last CTA scans them, apply)
 __device__ __forceinline__ bool eg_last_block(unsigned int *ticket)
