@@ -253,28 +253,15 @@ int kp_fetch_scratch(kp_ctx *ctx, size_t bytes)
     return kp_stream_wait(ctx);
 }
 
-// How a host thread waits for its stream.  Spinning (cudaStreamSynchronize) has the lowest latency and is right
-// while every waiting thread has a core of its own; when the ranks of one box together run more worker threads
-// than there are cores (8 GPUs x 4 frames in flight on a small host), spinning threads steal the cores the
-// launching threads need, so the wait sleeps on a blocking event instead.  KP_SYNC=spin|block overrides;
-// auto = block iff LOCAL_WORLD_SIZE x (KP_WORKERS_HINT + 1) exceeds 60 % of the cores (the pipeline sets the hint to
-// its worker count).
+// How a host thread waits for its stream: cudaStreamSynchronize.  The frame engine has one host thread per GPU and waits
+// once per call, so there is no wait policy to choose; `KP_SYNC=block` (an explicit request, e.g. many single-operation
+// callers sharing few cores) sleeps on a blocking event instead.  Nothing is inferred from the environment.
 static int kp_sync_blocking()
 {
     static int mode = -1;
     if (mode >= 0) return mode;
     const char *e = getenv("KP_SYNC");
-    if (e && !strcmp(e, "block")) return mode = 1;
-    if (e && !strcmp(e, "spin")) return mode = 0;
-    long cores = 0;
-    cpu_set_t set;
-    if (sched_getaffinity(0, sizeof set, &set) == 0) cores = CPU_COUNT(&set);
-    if (cores <= 0) cores = (long)std::thread::hardware_concurrency();
-    const char *lw = getenv("LOCAL_WORLD_SIZE");
-    const char *wh = getenv("KP_WORKERS_HINT");
-    const long ranks = lw ? atol(lw) : 1, workers = wh ? atol(wh) : 4;
-    // measured: 14 spinning workers on 24 cores scale 2.01 x over one GPU, 28 on 32 cores only 3.60 x over four
-    return mode = (cores > 0 && (ranks > 0 ? ranks : 1) * ((workers > 0 ? workers : 1) + 1) * 10 > cores * 6) ? 1 : 0;
+    return mode = (e && !strcmp(e, "block")) ? 1 : 0;
 }
 
 int kp_stream_wait(kp_ctx *ctx)
