@@ -541,7 +541,12 @@ def main():
             "frame_stats": {"n_fused": int(r0.n_fused), "n_voxel": int(r0.n_voxel), "n_sor": int(r0.n_sor),
                             "n_floor_inliers": int(r0.n_floor_inliers), "n_out": int(r0.n_out),
                             "icp_iters": [int(r0.icp_iters[i]) for i in range(2)],
-                            "icp_fitness": [round(float(r0.icp_fitness[i]), 4) for i in range(2)]},
+                            "icp_fitness": [round(float(r0.icp_fitness[i]), 4) for i in range(2)],
+                            # queries each level of the neighbour search hands on (SOR k=20, floor SOR k=50, normals)
+                            "knn_left_after_level0": stats.get("leftovers_l0") if stats else None,
+                            "knn_left_after_level1": stats.get("leftovers_l1") if stats else None,
+                            "n_merged": stats.get("n_merged") if stats else None,
+                            "n_icp_clouds": stats.get("n_icp") if stats else None},
         }
         icpv = fam.get("icp")
         if icpv:
