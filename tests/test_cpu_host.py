@@ -196,3 +196,17 @@ def test_bench_b200_arm_fails_loudly_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600)
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout) and not any(ln.startswith("{") for ln in r.stdout.splitlines())
+
+
+def test_bench_gives_every_rank_the_same_workload():
+    """Weak scaling needs the same per-GPU work on every rank: `bench.make_inputs` hands every rank the same distinct frames,
+    rotated by rank (a first version gave rank r its own window of the synthetic sequence; the windows differed by up to
+    11 % in cost and read as 0.91 scaling efficiency: profiles/r02_g_gpu_variance.json)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    base = bench.make_inputs("NFOV", 3, 0)
+    for rank in (1, 2, 5):
+        other = bench.make_inputs("NFOV", 3, rank)
+        assert np.array_equal(np.roll(base[1], -(rank % 3), axis=0), other[1])       # same frames, rotated
+        for a, b in zip(base[2:], other[2:]):
+            assert np.array_equal(a, b, equal_nan=True)                               # same tables and extrinsics
